@@ -1,0 +1,95 @@
+"""Pin both CPU oracles to the golden vectors produced by the real reference (CPU only)."""
+import numpy as np
+import pytest
+
+from conftest import Golden, golden_names, rel_l2
+from oracle import c_oracle, loop_oracle
+from snowmocap_b200 import synth
+
+TOL = 1e-10   # FP64 restatement vs reference (adjugate inverse instead of LAPACK getri)
+
+
+def _check(got, want, what):
+    pts, ks, ps = want
+    assert len(got[0]) == pts.shape[0], f"{what}: count {len(got[0])} != {pts.shape[0]}"
+    if pts.shape[0] == 0:
+        return
+    assert rel_l2(np.array(got[0]), pts) < TOL, what
+    # scores are ~1/dist: compare with a relative tolerance per element
+    np.testing.assert_allclose(np.array(got[1]), ks, rtol=1e-8, atol=1e-12, err_msg=what)
+    np.testing.assert_allclose(np.array(got[2]), ps, rtol=1e-8, atol=1e-12, err_msg=what)
+
+
+def test_loop_oracle_matches_reference(golden):
+    g, p = golden, golden.params
+    for f in range(g.F):
+        tri = loop_oracle.triangulate_frame(g.kpts[f], g.scores[f], g.counts[f], g.K, g.R, g.t,
+                                            kst=p["kst"], ast=p["ast"], dthr=p["dthr"])
+        _check((tri[loop_oracle.POINTS], tri[loop_oracle.KSCORES], tri[loop_oracle.PSCORES]), g.tri[f],
+               f"{g.name} frame {f} triangulate")
+        con = loop_oracle.condense_frame(tri, tol=p["cond_tol"], num_tol=p["num_tol"], score_tol=p["score_tol"],
+                                         center=p["center"], keypoint_num=p["keypoint_num"])
+        _check((con[loop_oracle.POINTS], con[loop_oracle.KSCORES], con[loop_oracle.PSCORES]), g.con[f],
+               f"{g.name} frame {f} condense")
+
+
+def test_c_oracle_candidates_match_reference(golden):
+    g, p = golden, golden.params
+    for f in range(g.F):
+        c = c_oracle.candidates(g.kpts[f], g.scores[f], g.counts[f], g.K, g.R, g.t, p["kst"], p["ast"], p["dthr"])
+        _check((c["points"], c["kscores"], c["pscores"]), g.tri[f], f"{g.name} frame {f}")
+
+
+def test_c_oracle_condense_matches_reference(golden):
+    g, p = golden, golden.params
+    for f in range(g.F):
+        pts, ks, _ = g.tri[f]
+        c = c_oracle.condense(pts, ks, p["cond_tol"], p["num_tol"], p["score_tol"], p["center"], p["keypoint_num"])
+        _check((c["points"], c["kscores"], c["pscores"]), g.con[f], f"{g.name} frame {f}")
+
+
+def test_c_oracle_fused_matches_reference(golden):
+    g, p = golden, golden.params
+    pout = max(1, max(c[0].shape[0] for c in g.con))
+    r = c_oracle.fused(g.kpts, g.scores, g.counts, g.K, g.R, g.t, p, Pout=pout, keypoint_num=p["keypoint_num"])
+    for f in range(g.F):
+        n = g.con[f][0].shape[0]
+        assert r["nout"][f] == n
+        assert r["ncand"][f] == g.tri[f][0].shape[0]
+        _check((r["points"][f, :n], r["kscores"][f, :n], r["pscores"][f, :n]), g.con[f], f"{g.name} frame {f}")
+
+
+def test_fused_threads_agree():
+    rig = synth.ring_rig(6)
+    d = synth.make_frames(rig, 24, 2, 17, seed=5, low_score_frac=0.1, drop_prob=0.1)
+    a = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, synth.MULTI_PARAMS, Pout=6, nthreads=1)
+    b = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, synth.MULTI_PARAMS, Pout=6, nthreads=4)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), k
+
+
+def test_skew_ray_known_answer():
+    # two perpendicular rays through (1,0,0)/(0,1,0) offset by 2 along z: midpoint z=1, distance 2
+    hm, hs = np.array([[1.0, 0, 0]]), np.array([[0, 1.0, 0]])
+    tm, ts = np.array([[-1.0, 0, 0]]), np.array([[0, -1.0, 2.0]])
+    dist, W = c_oracle.skew_ray(hm, hs, tm, ts)
+    assert abs(dist[0] - 2.0) < 1e-14 and np.allclose(W[0], [0, 0, 1.0], atol=1e-14)
+    d2, W2 = loop_oracle.skew_ray_solve(hm.T, hs.T, tm.T, ts.T)
+    assert abs(d2 - 2.0) < 1e-14 and np.allclose(W2, [0, 0, 1.0], atol=1e-14)
+
+
+def test_single_candidate_condense_is_empty():
+    # BASELINE config 1 (C=2, P=1) yields one candidate and zero condensed persons
+    g = Golden("cfg1_c2p1j17")
+    assert all(t[0].shape[0] == 1 for t in g.tri) and all(c[0].shape[0] == 0 for c in g.con)
+
+
+def test_noise_free_input_gives_nan_like_reference():
+    # exact projections -> dist==0 -> inf score -> NaN fused point (not special-cased)
+    rig = synth.ring_rig(3)
+    X = np.array([[[0.25, -0.5, 1.0]]])
+    uv = synth.project(rig, X)                     # (C,1,1,2) exact float64
+    hm = loop_oracle.back_project(rig.K[0], rig.R[0], uv[0, 0, 0])
+    hs = loop_oracle.back_project(rig.K[1], rig.R[1], uv[1, 0, 0])
+    dist, _ = loop_oracle.skew_ray_solve(hm, hs, rig.t[0].reshape(3, 1), rig.t[1].reshape(3, 1))
+    assert dist < 1e-12
