@@ -1,0 +1,115 @@
+/* snowtri.h -- C ABI of the B200-native multi-camera triangulation engine.
+ *
+ * This is the drop-in boundary for the one hot path of liaochikon/SnowMocap:
+ *     CameraGroup.add_human_2D_points   (reference snowvision/camera.py:234-253)
+ *  -> Human_Triangulation               (reference snowvision/triangulation.py:50-93)
+ *  -> Human_Triangulation_Condense      (reference snowvision/triangulation.py:95-162)
+ * The reference has no FFI of its own (it is pure Python); these entry points are what a
+ * ctypes binding inside snowvision would call.
+ *
+ * Conventions
+ *  - Every function returns 0 on success or a negative SNOWTRI_E_* code; no C++ exception
+ *    crosses this boundary.  snowtri_last_error() gives a human-readable message.
+ *  - All d_* arguments are DEVICE pointers owned by the caller, h_* are HOST pointers.
+ *    The library only allocates its own scratch.  Work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*, NULL = default stream) and is asynchronous unless noted.
+ *  - One handle per device; a handle is not thread-safe.
+ *  - Layouts (row-major, innermost last):
+ *      kpts    (F, C, P, J, 2) float32   undistorted pixel coordinates (u, v)
+ *      scores  (F, C, P, J)    float32   detector confidences
+ *      counts  (F, C)          int32     persons present per camera (slots [0,count) valid);
+ *                                        NULL means every camera sees P persons
+ *      cameras K (C,3,3), R (C,3,3) camera->world, t (C,3) camera centre; float64, host
+ *  - There is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef SNOWTRI_H_
+#define SNOWTRI_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct snowtri_handle snowtri_t;
+
+enum {
+    SNOWTRI_OK = 0,
+    SNOWTRI_E_ARG = -1,        /* bad argument (NULL, out-of-range index, misaligned pointer) */
+    SNOWTRI_E_CUDA = -2,       /* a CUDA runtime call failed */
+    SNOWTRI_E_UNSUPPORTED = -3,/* problem size not supported by this build */
+    SNOWTRI_E_NOMEM = -4
+};
+
+/* Compute precision of the fused path (snowtri_run*).  The candidate/condense entry points
+ * always compute in float64 like the reference. */
+enum {
+    SNOWTRI_PREC_F64 = 0,      /* float64 arithmetic throughout (default; matches the reference) */
+    SNOWTRI_PREC_F32 = 1       /* float32 arithmetic, float64 re-evaluation of decisions near a threshold */
+};
+
+/* Camera parameter container on the device; replaces Camera/CameraGroup's K, R, t
+ * (reference snowvision/camera.py:16-44, 141-157).  K, R, t are host float64. */
+int snowtri_create(snowtri_t** out, int device, int C, const double* K, const double* R, const double* t);
+int snowtri_destroy(snowtri_t* h);
+
+/* Thresholds: Human_Triangulation(keypoint_score_threshold, average_score_threshold,
+ * distance_threshold) and Human_Triangulation_Condense(condense_distance_tol,
+ * condense_person_num_tol, condense_score_tol, center_point_index)
+ * (reference snowvision/triangulation.py:50, 95-100; config keys
+ * configs/snowmocap_default_config.json:10-16). */
+int snowtri_set_params(snowtri_t* h, double kst, double ast, double dthr,
+                       double cond_tol, int num_tol, double score_tol, int center);
+int snowtri_set_precision(snowtri_t* h, int precision);
+/* Launch tuning for tests/benchmarks: frames staged per CTA iteration and CTA cap (0 = automatic). */
+int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas);
+
+/* Fused hot path for a batch of F frames: rays -> all camera-pair x person-pair candidates ->
+ * gating -> greedy clustering -> score-weighted fuse (main.py:55-71 for every frame).
+ *   keypoint_num  Condense's keypoint_num (<= J); output joints per person
+ *   Pout          output person slots per frame
+ *   d_out         (F, Pout, keypoint_num, 4) float32: x, y, z, keypoint score; unused slots zeroed
+ *   d_pscores     (F, Pout) float32 person score; unused slots zeroed
+ *   d_nout        (F) int32 persons the reference would emit (if > Pout the frame was truncated)
+ */
+int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts,
+                int F, int P, int J, int keypoint_num, int Pout,
+                float* d_out, float* d_pscores, int* d_nout, void* stream);
+
+/* Same through HOST buffers (pinned memory recommended): H2D copies, snowtri_run, D2H copies,
+ * then waits for completion.  This is the call a reference-side plugin makes. */
+int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, const int* h_counts,
+                     int F, int P, int J, int keypoint_num, int Pout,
+                     float* h_out, float* h_pscores, int* h_nout, void* stream);
+
+/* Human_Triangulation alone (reference snowvision/triangulation.py:50-93), float64 results.
+ * Candidates are written at their DENSE index n = ((pair*P + pm)*P + ps), pair enumerating
+ * (mc < sc) lexicographically, Nc = C*(C-1)/2*P*P per frame:
+ *   d_cand (F, Nc, J, 4) float64: x, y, z, gated score
+ *   d_avg  (F, Nc) float64 mean score (the reference's person score)
+ *   d_keep (F, Nc) int32   1 if the reference would append this candidate, else 0
+ * The reference's list order is increasing n over the kept candidates. */
+int snowtri_candidates(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts,
+                       int F, int P, int J, double* d_cand, double* d_avg, int* d_keep, void* stream);
+
+/* Human_Triangulation_Condense alone (reference snowvision/triangulation.py:95-162) on
+ * caller-supplied candidates, float64:
+ *   d_cand (F, N, J, 4) float64: x, y, z, score of candidate i in list order; d_ncand (F) int32 <= N
+ *   d_out  (F, Pout, keypoint_num, 4) float64; d_pscores (F, Pout) float64; d_nout (F) int32 */
+int snowtri_condense(snowtri_t* h, const double* d_cand, const int* d_ncand, int F, int N, int J,
+                     int keypoint_num, int Pout, double* d_out, double* d_pscores, int* d_nout,
+                     void* stream);
+
+/* Batched Skew_Ray_Solver (reference snowvision/triangulation.py:24-31): n independent ray pairs.
+ * d_hm, d_hs, d_tm, d_ts (n,3) float64 -> d_dist (n), d_mid (n,3). */
+int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs,
+                     const double* d_tm, const double* d_ts, double* d_dist, double* d_mid, void* stream);
+
+/* Introspection. */
+const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
+long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */
+int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group);
+int snowtri_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNOWTRI_H_ */

@@ -1,0 +1,18 @@
+"""snowmocap_b200 -- B200-native multi-camera triangulation behind the SnowMocap API.
+
+Drop-in names (reference ``snowvision.camera`` / ``snowvision.triangulation``):
+``Camera``, ``CameraGroup``, ``Skew_Ray_Solver``, ``Human_Triangulation``,
+``Human_Triangulation_Condense``.  Batch API: ``TriangulationEngine``, ``triangulate_batch``.
+Importing the package does not need a GPU; calling into it does (no CPU fallback).
+"""
+from .camera import Camera, CameraGroup  # noqa: F401
+
+_LAZY = {"TriangulationEngine": "engine", "triangulate_batch": "engine", "Skew_Ray_Solver": "triangulation",
+         "Human_Triangulation": "triangulation", "Human_Triangulation_Condense": "triangulation"}
+
+
+def __getattr__(name):
+    if name in _LAZY:
+        import importlib
+        return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
+    raise AttributeError(name)

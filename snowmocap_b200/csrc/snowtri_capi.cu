@@ -1,0 +1,386 @@
+// C ABI of the triangulation engine (declared in include/snowtri.h).  Host-side glue only:
+// argument checks, shared-memory layout, launches.  No exception leaves this file.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "snowtri.h"
+#include "snowtri_kernels.cuh"
+
+using namespace snowtri;
+
+struct snowtri_handle {
+    int device, C, sm_count, max_smem;
+    double* d_cam;  // (C,12) M = R*inv(K), t
+    Params prm;
+    int precision;
+    int tune_G, tune_ctas;
+    long long launches;
+    int last_grid, last_block, last_smem, last_G;
+    // device staging owned by the handle (snowtri_run_host only)
+    void* stage[6];
+    size_t stage_cap[6];
+    char err[512];
+};
+
+static char g_err[512] = "";
+
+static int fail(snowtri_t* h, int code, const char* fmt, ...) {
+    char* dst = h ? h->err : g_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, SNOWTRI_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+static void inv3(const double* m, double* o) {
+    const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    o[0] = (e * i - f * h) / det; o[1] = (c * h - b * i) / det; o[2] = (b * f - c * e) / det;
+    o[3] = (f * g - d * i) / det; o[4] = (a * i - c * g) / det; o[5] = (c * d - a * f) / det;
+    o[6] = (d * h - e * g) / det; o[7] = (b * g - a * h) / det; o[8] = (a * e - b * d) / det;
+}
+
+static void default_params(Params* p) {
+    // defaults of the reference signatures (triangulation.py:50, 95-100)
+    p->kst = 0.5; p->ast = 0.0; p->dthr = 0.05; p->cond_tol = 0.1; p->score_tol = 0.0;
+    p->kst_f = 0.5f; p->num_tol = 0; p->center = 18;
+}
+
+extern "C" int snowtri_version(void) { return 1; }
+
+extern "C" const char* snowtri_last_error(snowtri_t* h) { return h ? h->err : g_err; }
+
+extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* K, const double* R,
+                              const double* t) {
+    if (!out || !K || !R || !t) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_create: NULL argument");
+    if (C < 1 || C > 255) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_create: C=%d outside [1,255]", C);
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SNOWTRI_E_CUDA, "snowtri_create: no CUDA device (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_create: device %d of %d", device, ndev);
+    snowtri_t* h = (snowtri_t*)calloc(1, sizeof(snowtri_t));
+    if (!h) return fail(nullptr, SNOWTRI_E_NOMEM, "snowtri_create: out of host memory");
+    h->device = device;
+    h->C = C;
+    default_params(&h->prm);
+    h->precision = SNOWTRI_PREC_F64;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        free(h);
+        return fail(nullptr, SNOWTRI_E_CUDA, "snowtri_create: %s", cudaGetErrorString(e));
+    }
+    if (prop.major < 10) {
+        free(h);
+        return fail(nullptr, SNOWTRI_E_UNSUPPORTED, "snowtri_create: device sm_%d%d, this build is sm_100a only",
+                    prop.major, prop.minor);
+    }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    double* cam = (double*)malloc(sizeof(double) * 12 * C);
+    for (int c = 0; c < C; ++c) {
+        double Kinv[9];
+        inv3(K + 9 * c, Kinv);
+        for (int r = 0; r < 3; ++r)
+            for (int k = 0; k < 3; ++k) {
+                double s = 0;
+                for (int m = 0; m < 3; ++m) s += R[9 * c + 3 * r + m] * Kinv[3 * m + k];
+                cam[12 * c + 3 * r + k] = s;
+            }
+        for (int k = 0; k < 3; ++k) cam[12 * c + 9 + k] = t[3 * c + k];
+    }
+    e = cudaMalloc(&h->d_cam, sizeof(double) * 12 * C);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_cam, cam, sizeof(double) * 12 * C, cudaMemcpyHostToDevice);
+    free(cam);
+    if (e != cudaSuccess) {
+        if (h->d_cam) cudaFree(h->d_cam);
+        free(h);
+        return fail(nullptr, SNOWTRI_E_CUDA, "snowtri_create: %s", cudaGetErrorString(e));
+    }
+    cudaFuncSetAttribute(fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    cudaFuncSetAttribute(fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    cudaFuncSetAttribute(condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
+    *out = h;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_destroy(snowtri_t* h) {
+    if (!h) return SNOWTRI_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 6; ++i)
+        if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->d_cam) cudaFree(h->d_cam);
+    free(h);
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_set_params(snowtri_t* h, double kst, double ast, double dthr, double cond_tol, int num_tol,
+                                  double score_tol, int center) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_params: NULL handle");
+    if (center < 0) return fail(h, SNOWTRI_E_ARG, "snowtri_set_params: center_point_index %d < 0", center);
+    h->prm.kst = kst; h->prm.ast = ast; h->prm.dthr = dthr; h->prm.cond_tol = cond_tol;
+    h->prm.num_tol = num_tol; h->prm.score_tol = score_tol; h->prm.center = center;
+    float kf = (float)kst;
+    if ((double)kf < kst) kf = nextafterf(kf, INFINITY);
+    h->prm.kst_f = kf;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_precision: NULL handle");
+    if (precision != SNOWTRI_PREC_F64 && precision != SNOWTRI_PREC_F32)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_set_precision: unknown precision %d", precision);
+    h->precision = precision;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_tuning: NULL handle");
+    h->tune_G = frames_per_group > 0 ? frames_per_group : 0;
+    h->tune_ctas = max_ctas > 0 ? max_ctas : 0;
+    return SNOWTRI_OK;
+}
+
+extern "C" long long snowtri_launch_count(snowtri_t* h) { return h ? h->launches : 0; }
+
+extern "C" int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group) {
+    if (!h) return SNOWTRI_E_ARG;
+    if (grid) *grid = h->last_grid;
+    if (block) *block = h->last_block;
+    if (smem_bytes) *smem_bytes = h->last_smem;
+    if (frames_per_group) *frames_per_group = h->last_G;
+    return SNOWTRI_OK;
+}
+
+// Shared-memory layout of fused_kernel for G frames per group; returns total bytes.
+static size_t fused_layout(int C, int P, int J, int Jout, int Pout, int G, size_t tsz, FusedSmem* L) {
+    const size_t npairs = (size_t)C * (C - 1) / 2, ncand = npairs * P * P, R = (size_t)C * P * J;
+    size_t o = 16;  // mbarrier
+    auto take = [&](size_t bytes, size_t align) -> int {
+        o = (o + align - 1) / align * align;
+        const size_t r = o;
+        o += bytes;
+        return (int)r;
+    };
+    L->cam = take((size_t)C * 9 * tsz, 16);
+    L->pairs = take(npairs * 2, 4);
+    L->pd = take(npairs * 6 * tsz, 16);
+    L->stage_uv = take(G * R * 8, 128);
+    L->stage_s = take(G * R * 4, 128);
+    L->hx = take(G * R * tsz, 16);
+    L->hy = take(G * R * tsz, 16);
+    L->hz = take(G * R * tsz, 16);
+    L->sc = take(G * R * 4, 16);
+    L->cnt = take((size_t)G * C * 4, 4);
+    L->cen = take(G * ncand * 24, 8);
+    L->keep = take(G * ncand, 4);
+    L->ab = take(G * ncand, 4);
+    L->klist = take(G * ncand * 4, 4);
+    L->memb = take(G * ncand * 4, 4);
+    L->cstart = take(G * ncand * 4, 4);
+    L->cn = take(G * ncand * 4, 4);
+    L->ksum = take(G * ncand * 8, 8);
+    L->slot = take(G * ncand * 4, 4);
+    L->kcount = take((size_t)G * 2 * 4, 4);
+    L->ks = take((size_t)G * Pout * Jout * tsz, 16);
+    L->total = (int)o;
+    return o;
+}
+
+extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F,
+                           int P, int J, int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout,
+                           void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_run: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if (!d_kpts || !d_scores || !d_out || !d_pscores || !d_nout) return fail(h, SNOWTRI_E_ARG, "snowtri_run: NULL buffer");
+    if (F < 0 || P < 1 || P > 255 || J < 1 || Pout < 1)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_run: bad sizes F=%d P=%d J=%d Pout=%d", F, P, J, Pout);
+    if (keypoint_num < 1 || keypoint_num > J)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_run: keypoint_num=%d must be in [1, J=%d] (the reference raises IndexError above J)",
+                    keypoint_num, J);
+    if (h->prm.center >= J)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_run: center_point_index=%d >= J=%d (the reference raises IndexError)",
+                    h->prm.center, J);
+    if (((uintptr_t)d_out & 15u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_run: d_out must be 16-byte aligned");
+    if (((uintptr_t)d_kpts & 7u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_run: d_kpts must be 8-byte aligned");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+
+    const int C = h->C;
+    const size_t tsz = h->precision == SNOWTRI_PREC_F32 ? 4 : 8;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
+    a.out = d_out; a.pscores = d_pscores; a.nout = d_nout; a.cam = h->d_cam;
+    a.F = F; a.C = C; a.P = P; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
+    a.npairs = C * (C - 1) / 2;
+    a.ncand = a.npairs * P * P;
+    a.R = C * P * J;
+    a.prm = h->prm;
+    a.all_kept = (h->prm.ast <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
+    a.never_filter = (h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
+
+    // frames per group: as many as fit in shared memory (<= 32), preferring TMA-aligned groups
+    int Gmax = h->tune_G > 0 ? h->tune_G : 32;
+    if (Gmax > F) Gmax = F;
+    int G = 0;
+    for (int g = Gmax; g >= 1; --g)
+        if (fused_layout(C, P, J, a.Jout, Pout, g, tsz, &a.sm) <= (size_t)h->max_smem) { G = g; break; }
+    if (G == 0)
+        return fail(h, SNOWTRI_E_UNSUPPORTED,
+                    "snowtri_run: one frame (C=%d P=%d J=%d Pout=%d) needs %zu B of shared memory, device allows %d",
+                    C, P, J, Pout, fused_layout(C, P, J, a.Jout, Pout, 1, tsz, &a.sm), h->max_smem);
+    if (h->tune_G == 0) {
+        // keep at least ~4 groups per SM when the batch is large enough, and prefer (G*R)%4==0
+        while (G > 1 && (F + G - 1) / G < 4 * h->sm_count) --G;
+        for (int g = G; g >= 1 && g > G - 4; --g)
+            if (((size_t)g * a.R) % 4 == 0) { G = g; break; }
+    }
+    fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm);
+    a.G = G;
+    const bool aligned = (((uintptr_t)d_kpts & 15u) == 0) && (((uintptr_t)d_scores & 15u) == 0);
+    a.use_tma = (aligned && ((size_t)G * a.R) % 4 == 0) ? 1 : 0;
+
+    const int ngroups = (F + G - 1) / G;
+    int grid = ngroups < h->sm_count ? ngroups : h->sm_count;
+    if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->precision == SNOWTRI_PREC_F32)
+        fused_kernel<float><<<grid, kThreads, a.sm.total, st>>>(a);
+    else
+        fused_kernel<double><<<grid, kThreads, a.sm.total, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    h->last_grid = grid; h->last_block = kThreads; h->last_smem = a.sm.total; h->last_G = G;
+    return SNOWTRI_OK;
+}
+
+static int ensure_stage(snowtri_t* h, int i, size_t bytes) {
+    if (h->stage_cap[i] >= bytes) return SNOWTRI_OK;
+    if (h->stage[i]) cudaFree(h->stage[i]);
+    h->stage[i] = nullptr;
+    h->stage_cap[i] = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stage[i], bytes));
+    h->stage_cap[i] = bytes;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, const int* h_counts, int F,
+                                int P, int J, int keypoint_num, int Pout, float* h_out, float* h_pscores, int* h_nout,
+                                void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_run_host: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if (!h_kpts || !h_scores || !h_out || !h_pscores || !h_nout || F < 0 || P < 1 || J < 1 || Pout < 1 ||
+        keypoint_num < 1)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_run_host: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t rays = (size_t)F * h->C * P * J, outs = (size_t)F * Pout * keypoint_num;
+    const size_t need[6] = {rays * 8, rays * 4, (size_t)F * h->C * 4, outs * 16, (size_t)F * Pout * 4, (size_t)F * 4};
+    for (int i = 0; i < 6; ++i) {
+        int rc = ensure_stage(h, i, need[i]);
+        if (rc) return rc;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], h_kpts, need[0], cudaMemcpyHostToDevice, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h->stage[1], h_scores, need[1], cudaMemcpyHostToDevice, st));
+    if (h_counts) CUDA_TRY(h, cudaMemcpyAsync(h->stage[2], h_counts, need[2], cudaMemcpyHostToDevice, st));
+    int rc = snowtri_run(h, (const float*)h->stage[0], (const float*)h->stage[1],
+                         h_counts ? (const int*)h->stage[2] : nullptr, F, P, J, keypoint_num, Pout,
+                         (float*)h->stage[3], (float*)h->stage[4], (int*)h->stage[5], stream);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h_out, h->stage[3], need[3], cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h_pscores, h->stage[4], need[4], cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaMemcpyAsync(h_nout, h->stage[5], need[5], cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_candidates(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F,
+                                  int P, int J, double* d_cand, double* d_avg, int* d_keep, void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_candidates: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if (!d_kpts || !d_scores || !d_cand || !d_avg || !d_keep || F < 0 || P < 1 || P > 255 || J < 1)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_candidates: bad argument");
+    if (((uintptr_t)d_cand & 15u) != 0 || ((uintptr_t)d_kpts & 7u) != 0)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_candidates: misaligned buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CandArgs a;
+    memset(&a, 0, sizeof(a));
+    a.cam = h->d_cam;
+    a.C = h->C; a.P = P; a.J = J;
+    a.npairs = h->C * (h->C - 1) / 2;
+    a.ncand = a.npairs * P * P;
+    a.prm = h->prm;
+    if (a.ncand == 0) return SNOWTRI_OK;
+    const int chunk = 32768;
+    for (int f0 = 0; f0 < F; f0 += chunk) {
+        const int fc = F - f0 < chunk ? F - f0 : chunk;
+        const size_t ro = (size_t)f0 * h->C * P * J, co = (size_t)f0 * a.ncand;
+        a.kpts = d_kpts + ro * 2;
+        a.scores = d_scores + ro;
+        a.counts = d_counts ? d_counts + (size_t)f0 * h->C : nullptr;
+        a.cand = d_cand + co * J * 4;
+        a.avg = d_avg + co;
+        a.keep = d_keep + co;
+        a.F = fc;
+        dim3 grid((a.ncand + kWarps - 1) / kWarps, fc);
+        candidates_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(a);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_condense(snowtri_t* h, const double* d_cand, const int* d_ncand, int F, int N, int J,
+                                int keypoint_num, int Pout, double* d_out, double* d_pscores, int* d_nout,
+                                void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_condense: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if (!d_ncand || !d_out || !d_pscores || !d_nout || F < 0 || N < 0 || J < 1 || Pout < 1 || (N > 0 && !d_cand))
+        return fail(h, SNOWTRI_E_ARG, "snowtri_condense: bad argument");
+    if (keypoint_num < 1 || keypoint_num > J)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_condense: keypoint_num=%d must be in [1, J=%d] (the reference raises IndexError above J)",
+                    keypoint_num, J);
+    if (N > 1 && h->prm.center >= J)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_condense: center_point_index=%d >= J=%d (the reference raises IndexError)",
+                    h->prm.center, J);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t smem = (size_t)N * 29 + 64;
+    if (smem > (size_t)h->max_smem)
+        return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_condense: N=%d candidates need %zu B of shared memory (max %d)", N,
+                    smem, h->max_smem);
+    CondArgs a;
+    a.cand = d_cand; a.ncand = d_ncand; a.out = d_out; a.pscores = d_pscores; a.nout = d_nout;
+    a.F = F; a.N = N; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
+    a.prm = h->prm;
+    condense_kernel<<<F, kThreads, smem, (cudaStream_t)stream>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs, const double* d_tm,
+                                const double* d_ts, double* d_dist, double* d_mid, void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_skew_ray: NULL handle");
+    if (n == 0) return SNOWTRI_OK;
+    if (n < 0 || !d_hm || !d_hs || !d_tm || !d_ts || !d_dist || !d_mid) return fail(h, SNOWTRI_E_ARG, "snowtri_skew_ray: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    skew_ray_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, d_hm, d_hs, d_tm, d_ts, d_dist, d_mid);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return SNOWTRI_OK;
+}

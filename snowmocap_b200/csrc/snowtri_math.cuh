@@ -1,0 +1,165 @@
+// Device math of the triangulation path, templated on the compute type T (double or float).
+//
+// Reference algebra being evaluated (reference snowvision/triangulation.py:24-31, 72-74):
+//   H = [hm hs],  S = (H^T H)^-1 H^T d,  d = ts - tm
+//   Wm = tm + hm*S0,  Ws = ts - hs*S1,  dist = |Wm - Ws|,  W = (Wm + Ws)/2
+//   score = ((sm + ss)/2) / (dist*1000), zeroed when sm<kst or ss<kst or dist>dthr
+// Closed form used here (no division by the 2x2 determinant on the hot path):
+//   A=hm.hm  Cc=hs.hs  B=hm.hs  D=hm.d  E=hs.d
+//   det = A*Cc - B^2 (>0)   n0 = Cc*D - B*E = det*S0   n1 = A*E - B*D = det*S1
+//   q   = hm*n0 + hs*n1 - d*det = det*(Wm - Ws)            => dist = |q|/det
+//   v   = hm*n0 - hs*n1                                     => W = mid + v/(2*det), mid=(tm+ts)/2
+//   score = (sm+ss)*0.0005*det*rsqrt(q.q)
+//   score*(W - mid) = (sm+ss)*0.00025*rsqrt(q.q) * v        (what the fuse step accumulates)
+//   dist > dthr  <=>  q.q > (dthr*det)^2
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace snowtri {
+
+template <typename T>
+struct V3 {
+    T x, y, z;
+};
+
+template <typename T>
+__device__ __forceinline__ T dot3(const V3<T>& a, const V3<T>& b) {
+    return fma(a.x, b.x, fma(a.y, b.y, a.z * b.z));
+}
+
+// 1/sqrt(x).  double: MUFU.RSQ64H seed (~2^-22) + two Newton steps (~1 ulp); float: MUFU.RSQ.
+__device__ __forceinline__ float rsqrt_t(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rsqrt_t(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double t = x * r;
+    double e = fma(-t, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    t = x * r;
+    e = fma(-t, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+
+// 1/x for positive finite x.  double: MUFU.RCP64H seed + two Newton steps; float: MUFU.RCP + one step.
+__device__ __forceinline__ float rcp_t(float x) {
+    float r = __frcp_rn(x);
+    return r;
+}
+__device__ __forceinline__ double rcp_t(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
+template <typename T>
+struct PairSol {
+    T det, n0, n1, qq;
+};
+
+template <typename T>
+__device__ __forceinline__ PairSol<T> pair_solve(const V3<T>& hm, const V3<T>& hs, const V3<T>& d) {
+    const T A = dot3(hm, hm), Cc = dot3(hs, hs), B = dot3(hm, hs);
+    const T D = dot3(hm, d), E = dot3(hs, d);
+    PairSol<T> s;
+    s.det = fma(A, Cc, -(B * B));
+    s.n0 = fma(Cc, D, -(B * E));
+    s.n1 = fma(A, E, -(B * D));
+    const T qx = fma(hm.x, s.n0, fma(hs.x, s.n1, -(d.x * s.det)));
+    const T qy = fma(hm.y, s.n0, fma(hs.y, s.n1, -(d.y * s.det)));
+    const T qz = fma(hm.z, s.n0, fma(hs.z, s.n1, -(d.z * s.det)));
+    s.qq = fma(qx, qx, fma(qy, qy, qz * qz));
+    return s;
+}
+
+// g = gated (sm+ss)*0.00025*rsqrt(q.q); the reference's score is 2*g*det.
+template <typename T>
+__device__ __forceinline__ T gated_g(const PairSol<T>& s, float sm, float ss, float kst_f, T dthr) {
+    const T thr = dthr * s.det;
+    const T r = rsqrt_t(s.qq);
+    T g = ((T)sm + (T)ss) * (r * (T)0.00025);
+    // same comparisons as the reference (strict; NaN distance is not gated)
+    if (sm < kst_f || ss < kst_f || s.qq > thr * thr) g = (T)0;
+    return g;
+}
+
+template <typename T>
+__device__ __forceinline__ V3<T> pair_v(const PairSol<T>& s, const V3<T>& hm, const V3<T>& hs) {
+    V3<T> v;
+    v.x = fma(hm.x, s.n0, -(hs.x * s.n1));
+    v.y = fma(hm.y, s.n0, -(hs.y * s.n1));
+    v.z = fma(hm.z, s.n0, -(hs.z * s.n1));
+    return v;
+}
+
+// Explicit midpoint W = mid + v/(2 det) (needed for clustering centres and candidate output).
+template <typename T>
+__device__ __forceinline__ V3<T> pair_midpoint(const PairSol<T>& s, const V3<T>& hm, const V3<T>& hs,
+                                               const V3<T>& mid) {
+    const V3<T> v = pair_v(s, hm, hs);
+    const T h = (T)0.5 * rcp_t(s.det);
+    V3<T> w;
+    w.x = fma(v.x, h, mid.x);
+    w.y = fma(v.y, h, mid.y);
+    w.z = fma(v.z, h, mid.z);
+    return w;
+}
+
+// Back-projection f = (R K^-1) [u v 1]^T (reference snowvision/camera.py:240-244); M row-major 3x3.
+template <typename T>
+__device__ __forceinline__ V3<T> back_project(const T* __restrict__ M, T u, T v) {
+    V3<T> h;
+    h.x = fma(M[0], u, fma(M[1], v, M[2]));
+    h.y = fma(M[3], u, fma(M[4], v, M[5]));
+    h.z = fma(M[6], u, fma(M[7], v, M[8]));
+    return h;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA) -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+
+}  // namespace snowtri

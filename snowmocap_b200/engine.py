@@ -1,0 +1,202 @@
+"""Batch API of the triangulation engine: torch tensors as device memory, ctypes into the C ABI.
+
+``TriangulationEngine.run`` is the fused hot path (rays -> candidates -> clustering -> fuse,
+i.e. reference ``main.py:55-71`` for every frame of a batch) and what the benchmark times.
+PyTorch is used for allocation, streams and host<->device copies only.
+"""
+from __future__ import annotations
+
+import ctypes as ct
+
+import numpy as np
+import torch
+
+from . import _lib
+
+PARAM_KEYS = ("kst", "ast", "dthr", "cond_tol", "num_tol", "score_tol", "center")
+# defaults of the reference signatures (snowvision/triangulation.py:50, 95-100)
+REFERENCE_DEFAULTS = dict(kst=0.5, ast=0.0, dthr=0.05, cond_tol=0.1, num_tol=0, score_tol=0.0, center=18)
+# reference config keys (configs/snowmocap_default_config.json:10-16) -> engine parameter names
+CONFIG_KEYS = {"keypoint_score_threshold": "kst", "average_score_threshold": "ast", "distance_threshold": "dthr",
+               "condense_distance_tol": "cond_tol", "condense_person_num_tol": "num_tol",
+               "condense_score_tol": "score_tol", "center_point_index": "center"}
+
+
+def _ptr(t):
+    return ct.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _np_ptr(a):
+    return ct.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def _stream():
+    return ct.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class TriangulationEngine:
+    """One handle per device holding the camera parameters (K, R camera->world, t camera centre)."""
+
+    def __init__(self, K, R, t, device=0, precision="f64", **params):
+        self._h = ct.c_void_p()
+        self._lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("snowmocap_b200 needs a CUDA device; there is no CPU fallback")
+        K = np.ascontiguousarray(K, np.float64).reshape(-1, 3, 3)
+        R = np.ascontiguousarray(R, np.float64).reshape(-1, 3, 3)
+        t = np.ascontiguousarray(t, np.float64).reshape(-1, 3)
+        if not (K.shape[0] == R.shape[0] == t.shape[0]):
+            raise ValueError("K, R, t must describe the same number of cameras")
+        self.C = int(K.shape[0])
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_create(ct.byref(self._h), self.device.index, self.C,
+                                                _np_ptr(K), _np_ptr(R), _np_ptr(t)))
+        self.params = dict(REFERENCE_DEFAULTS)
+        self.set_params(**params)
+        self.set_precision(precision)
+
+    # -- configuration ---------------------------------------------------------------------
+    def set_params(self, **params):
+        for k, v in params.items():
+            k = CONFIG_KEYS.get(k, k)
+            if k not in PARAM_KEYS:
+                raise TypeError(f"unknown triangulation parameter {k!r}")
+            self.params[k] = v
+        p = self.params
+        _lib.check(self._lib.snowtri_set_params(self._h, float(p["kst"]), float(p["ast"]), float(p["dthr"]),
+                                                float(p["cond_tol"]), int(p["num_tol"]), float(p["score_tol"]),
+                                                int(p["center"])), self._h)
+
+    def set_precision(self, precision):
+        code = {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32}[precision]
+        _lib.check(self._lib.snowtri_set_precision(self._h, code), self._h)
+        self.precision = precision
+
+    def set_tuning(self, frames_per_group=0, max_ctas=0):
+        _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas)), self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.snowtri_launch_count(self._h))
+
+    def last_launch_info(self):
+        g, b, s, fg = ct.c_int(), ct.c_int(), ct.c_int(), ct.c_int()
+        self._lib.snowtri_last_launch_info(self._h, ct.byref(g), ct.byref(b), ct.byref(s), ct.byref(fg))
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "frames_per_group": fg.value}
+
+    def close(self):
+        if self._h:
+            self._lib.snowtri_destroy(self._h)
+            self._h = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- helpers ---------------------------------------------------------------------------
+    def _check_inputs(self, kpts, scores, counts):
+        if kpts.dim() != 5 or kpts.shape[-1] != 2 or scores.shape != kpts.shape[:-1]:
+            raise ValueError("expected kpts (F,C,P,J,2) and scores (F,C,P,J)")
+        F, C, P, J = scores.shape
+        if C != self.C:
+            raise ValueError(f"batch has {C} cameras, engine was built for {self.C}")
+        for name, x, dt in (("kpts", kpts, torch.float32), ("scores", scores, torch.float32)):
+            if x.dtype != dt or not x.is_cuda or not x.is_contiguous() or x.device != self.device:
+                raise ValueError(f"{name} must be a contiguous {dt} tensor on {self.device}")
+        if counts is not None:
+            if counts.shape != (F, C) or counts.dtype != torch.int32 or not counts.is_cuda or not counts.is_contiguous():
+                raise ValueError("counts must be a contiguous int32 cuda tensor of shape (F,C)")
+        return F, C, P, J
+
+    # -- fused hot path --------------------------------------------------------------------
+    def run(self, kpts, scores, counts=None, Pout=None, keypoint_num=None, out=None):
+        """Fused path on device tensors.  Returns dict(out (F,Pout,Jout,4) f32 [x,y,z,score],
+        pscores (F,Pout) f32, nout (F,) i32).  Asynchronous on the current stream."""
+        F, C, P, J = self._check_inputs(kpts, scores, counts)
+        Jout = J if keypoint_num is None else int(keypoint_num)
+        Pout = P if Pout is None else int(Pout)
+        if out is None:
+            out = {"out": torch.empty((F, Pout, Jout, 4), dtype=torch.float32, device=self.device),
+                   "pscores": torch.empty((F, Pout), dtype=torch.float32, device=self.device),
+                   "nout": torch.empty((F,), dtype=torch.int32, device=self.device)}
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_run(self._h, _ptr(kpts), _ptr(scores), _ptr(counts), F, P, J, Jout, Pout,
+                                             _ptr(out["out"]), _ptr(out["pscores"]), _ptr(out["nout"]), _stream()),
+                       self._h)
+        return out
+
+    def run_host(self, kpts, scores, counts=None, Pout=None, keypoint_num=None, out=None):
+        """Fused path through HOST numpy buffers (H2D + kernel + D2H inside the C call, synchronous)."""
+        kpts = np.ascontiguousarray(kpts, np.float32)
+        scores = np.ascontiguousarray(scores, np.float32)
+        F, C, P, J = scores.shape
+        if C != self.C or kpts.shape != (F, C, P, J, 2):
+            raise ValueError("expected kpts (F,C,P,J,2) and scores (F,C,P,J) for this engine's cameras")
+        if counts is not None:
+            counts = np.ascontiguousarray(counts, np.int32).reshape(F, C)
+        Jout = J if keypoint_num is None else int(keypoint_num)
+        Pout = P if Pout is None else int(Pout)
+        if out is None:
+            out = {"out": np.empty((F, Pout, Jout, 4), np.float32), "pscores": np.empty((F, Pout), np.float32),
+                   "nout": np.empty((F,), np.int32)}
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_run_host(self._h, _np_ptr(kpts), _np_ptr(scores), _np_ptr(counts), F, P, J,
+                                                  Jout, Pout, _np_ptr(out["out"]), _np_ptr(out["pscores"]),
+                                                  _np_ptr(out["nout"]), _stream()), self._h)
+        return out
+
+    # -- the two reference functions separately (float64) ----------------------------------
+    def candidates(self, kpts, scores, counts=None):
+        """Human_Triangulation for every frame: dict(cand (F,Nc,J,4) f64, avg (F,Nc) f64, keep (F,Nc) i32),
+        dense candidate index n = ((pair*P + pm)*P + ps)."""
+        F, C, P, J = self._check_inputs(kpts, scores, counts)
+        nc = C * (C - 1) // 2 * P * P
+        res = {"cand": torch.zeros((F, nc, J, 4), dtype=torch.float64, device=self.device),
+               "avg": torch.zeros((F, nc), dtype=torch.float64, device=self.device),
+               "keep": torch.zeros((F, nc), dtype=torch.int32, device=self.device)}
+        if nc:
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.snowtri_candidates(self._h, _ptr(kpts), _ptr(scores), _ptr(counts), F, P, J,
+                                                        _ptr(res["cand"]), _ptr(res["avg"]), _ptr(res["keep"]),
+                                                        _stream()), self._h)
+        return res
+
+    def condense(self, cand, ncand, keypoint_num=None, Pout=None):
+        """Human_Triangulation_Condense on materialised candidates cand (F,N,J,4) f64, ncand (F,) i32."""
+        if cand.dim() != 4 or cand.shape[-1] != 4 or cand.dtype != torch.float64 or not cand.is_contiguous():
+            raise ValueError("cand must be a contiguous float64 tensor of shape (F,N,J,4)")
+        F, N, J, _ = cand.shape
+        Jout = J if keypoint_num is None else int(keypoint_num)
+        Pout = max(1, N) if Pout is None else int(Pout)
+        res = {"out": torch.empty((F, Pout, Jout, 4), dtype=torch.float64, device=self.device),
+               "pscores": torch.empty((F, Pout), dtype=torch.float64, device=self.device),
+               "nout": torch.empty((F,), dtype=torch.int32, device=self.device)}
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_condense(self._h, _ptr(cand), _ptr(ncand), F, N, J, Jout, Pout,
+                                                  _ptr(res["out"]), _ptr(res["pscores"]), _ptr(res["nout"]),
+                                                  _stream()), self._h)
+        return res
+
+    def skew_ray(self, hm, hs, tm, ts):
+        """Batched Skew_Ray_Solver on (n,3) float64 cuda tensors -> (dist (n,), mid (n,3))."""
+        n = hm.shape[0]
+        dist = torch.empty((n,), dtype=torch.float64, device=self.device)
+        mid = torch.empty((n, 3), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_skew_ray(self._h, n, _ptr(hm), _ptr(hs), _ptr(tm), _ptr(ts), _ptr(dist),
+                                                  _ptr(mid), _stream()), self._h)
+        return dist, mid
+
+
+def triangulate_batch(kpts, scores, counts, K, R, t, Pout=None, keypoint_num=None, precision="f64", **params):
+    """One-shot convenience wrapper: build an engine, run the fused path, return its result dict."""
+    eng = TriangulationEngine(K, R, t, device=kpts.device.index or 0, precision=precision, **params)
+    try:
+        res = eng.run(kpts, scores, counts, Pout=Pout, keypoint_num=keypoint_num)
+        torch.cuda.synchronize(kpts.device)
+    finally:
+        eng.close()
+    return res

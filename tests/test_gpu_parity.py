@@ -1,0 +1,270 @@
+"""Parity of the CUDA path against the golden vectors and the CPU oracles (run on the B200 box).
+
+Tolerances: the candidate/condense entry points compute and return float64 -> 1e-9 relative L2
+against the reference.  The fused path computes in float64 but stores float32 -> 1e-6.  The
+north_star bound for the fused path in any precision mode is 1e-4 relative L2 on the 3D points.
+"""
+import numpy as np
+import pytest
+
+from conftest import Golden, floor_rig, golden_names, rel_l2
+from snowmocap_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64 = 1e-9
+TOL_FUSED = 1e-6
+TOL_NORTH_STAR = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    return torch
+
+
+def _engine(g_or_rig, params, precision="f64"):
+    from snowmocap_b200.engine import TriangulationEngine
+    p = {k: v for k, v in params.items() if k != "keypoint_num"}
+    return TriangulationEngine(g_or_rig.K, g_or_rig.R, g_or_rig.t, device=0, precision=precision, **p)
+
+
+def _to_dev(torch, *arrays):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrays]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_fused_matches_reference_golden(torch_cuda, name):
+    torch = torch_cuda
+    g = Golden(name)
+    eng = _engine(g, g.params)
+    pout = max(1, max(c[0].shape[0] for c in g.con))
+    kp, sc, cn = _to_dev(torch, g.kpts, g.scores, g.counts)
+    res = eng.run(kp, sc, cn, Pout=pout, keypoint_num=g.params["keypoint_num"])
+    torch.cuda.synchronize()
+    out, ps, nout = res["out"].cpu().numpy(), res["pscores"].cpu().numpy(), res["nout"].cpu().numpy()
+    for f in range(g.F):
+        pts, ks, pscore = g.con[f]
+        n = pts.shape[0]
+        assert nout[f] == n, f"{name} frame {f}: persons {nout[f]} != {n}"
+        if n:
+            assert rel_l2(out[f, :n, :, :3], pts) < TOL_FUSED
+            np.testing.assert_allclose(out[f, :n, :, 3], ks, rtol=1e-5, atol=1e-7)
+            np.testing.assert_allclose(ps[f, :n], pscore, rtol=1e-5, atol=1e-7)
+        assert not out[f, n:].any() and not ps[f, n:].any(), "unused slots must be zero"
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_candidates_match_reference_golden(torch_cuda, name):
+    torch = torch_cuda
+    g = Golden(name)
+    eng = _engine(g, g.params)
+    kp, sc, cn = _to_dev(torch, g.kpts, g.scores, g.counts)
+    res = eng.candidates(kp, sc, cn)
+    torch.cuda.synchronize()
+    cand, avg, keep = res["cand"].cpu().numpy(), res["avg"].cpu().numpy(), res["keep"].cpu().numpy().astype(bool)
+    for f in range(g.F):
+        pts, ks, pscore = g.tri[f]
+        assert keep[f].sum() == pts.shape[0]
+        if pts.shape[0]:
+            assert rel_l2(cand[f][keep[f]][:, :, :3], pts) < TOL_F64
+            np.testing.assert_allclose(cand[f][keep[f]][:, :, 3], ks, rtol=1e-8, atol=1e-12)
+            np.testing.assert_allclose(avg[f][keep[f]], pscore, rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_condense_matches_reference_golden(torch_cuda, name):
+    torch = torch_cuda
+    g = Golden(name)
+    eng = _engine(g, g.params)
+    nmax = max(1, max(t[0].shape[0] for t in g.tri))
+    J = g.kpts.shape[3]
+    cand = np.zeros((g.F, nmax, J, 4))
+    ncand = np.zeros(g.F, np.int32)
+    for f in range(g.F):
+        n = g.tri[f][0].shape[0]
+        ncand[f] = n
+        cand[f, :n, :, :3] = g.tri[f][0]
+        cand[f, :n, :, 3] = g.tri[f][1]
+    dc, dn = _to_dev(torch, cand, ncand)
+    res = eng.condense(dc, dn, keypoint_num=g.params["keypoint_num"], Pout=nmax)
+    torch.cuda.synchronize()
+    out, ps, nout = res["out"].cpu().numpy(), res["pscores"].cpu().numpy(), res["nout"].cpu().numpy()
+    for f in range(g.F):
+        pts, ks, pscore = g.con[f]
+        n = pts.shape[0]
+        assert nout[f] == n
+        if n:
+            assert rel_l2(out[f, :n, :, :3], pts) < TOL_F64
+            np.testing.assert_allclose(out[f, :n, :, 3], ks, rtol=1e-9, atol=1e-13)
+            np.testing.assert_allclose(ps[f, :n], pscore, rtol=1e-9, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_dropin_api_matches_reference_golden(torch_cuda, name):
+    """The reference's own call sequence (main.py:55-71, 106) through the drop-in names."""
+    import snowmocap_b200 as sv
+    g, p = Golden(name), Golden(name).params
+    C = g.K.shape[0]
+    group = sv.CameraGroup(cap_ids=list(range(C)), resolutions=[(1280, 720)] * C)
+    for c in range(C):
+        group.cameras[c].K, group.cameras[c].R, group.cameras[c].t = g.K[c], g.R[c], g.t[c].reshape(3, 1)
+    for f in range(g.F):
+        for c in range(C):
+            for q in range(int(g.counts[f, c])):
+                group.add_human_2D_points(g.kpts[f, c, q], g.scores[f, c, q], c)
+        tri = sv.Human_Triangulation(group, keypoint_score_threshold=p["kst"], average_score_threshold=p["ast"],
+                                     distance_threshold=p["dthr"])
+        con = sv.Human_Triangulation_Condense(tri, condense_distance_tol=p["cond_tol"],
+                                              condense_person_num_tol=p["num_tol"], condense_score_tol=p["score_tol"],
+                                              center_point_index=p["center"], keypoint_num=p["keypoint_num"])
+        group.clear_2D_points()
+        for got, want in ((tri, g.tri[f]), (con, g.con[f])):
+            assert set(got) == {"hrnet_triangulate_points", "hrnet_triangulate_keypoint_scores",
+                                "hrnet_triangulate_person_scores"}
+            n = want[0].shape[0]
+            assert len(got["hrnet_triangulate_points"]) == n
+            if n:
+                assert got["hrnet_triangulate_points"][0].dtype == np.float64
+                assert rel_l2(np.array(got["hrnet_triangulate_points"]), want[0]) < TOL_F64
+                np.testing.assert_allclose(np.array(got["hrnet_triangulate_keypoint_scores"]), want[1], rtol=1e-8, atol=1e-12)
+                np.testing.assert_allclose(np.array(got["hrnet_triangulate_person_scores"]), want[2], rtol=1e-8, atol=1e-12)
+
+
+CASES = [
+    # rig, F, P, J, params, Pout, data kwargs
+    ("floor2", 300, 1, 17, synth.DEFAULT_PARAMS, 2, {}),                       # BASELINE configs[0]
+    ("floor4", 1500, 1, 133, synth.DEFAULT_PARAMS, 2, {}),                     # BASELINE configs[1]
+    ("ring8", 120, 4, 133, synth.MULTI_PARAMS, 8, {}),                         # BASELINE configs[2] geometry
+    ("ring8", 60, 4, 133, synth.MULTI_PARAMS, 8, {"low_score_frac": 0.1, "drop_prob": 0.15}),
+    ("ring6", 200, 3, 17, dict(synth.MULTI_PARAMS, ast=0.0), 64, {"low_score_frac": 0.2}),   # ghost clusters
+    ("ring6", 200, 3, 17, dict(synth.MULTI_PARAMS, score_tol=0.3, num_tol=2, center=4), 8, {"low_score_frac": 0.1}),
+    ("ring5", 150, 2, 33, dict(synth.MULTI_PARAMS, kst=-1.0, ast=-5.0), 16, {}),              # kst<0: general paths
+]
+
+
+def _rig(name):
+    if name.startswith("floor"):
+        return floor_rig().subset(int(name[5:]))
+    return synth.ring_rig(int(name[4:]))
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("tuning", [(0, 0), (1, 3), (5, 7)])
+def test_fused_matches_c_oracle(torch_cuda, case, tuning):
+    """Seeded synthetic batches vs the C oracle, with different frames-per-group / CTA counts
+    (exercises the TMA and the plain-load staging paths, group tails and the persistent loop)."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rname, F, P, J, prm, pout, kw = CASES[case]
+    rig = _rig(rname)
+    d = synth.make_frames(rig, F, P, J, seed=100 + case, **kw)
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    eng = _engine(rig, prm)
+    eng.set_tuning(*tuning)
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    res = eng.run(kp, sc, cn, Pout=pout)
+    torch.cuda.synchronize()
+    out, ps, nout = res["out"].cpu().numpy(), res["pscores"].cpu().numpy(), res["nout"].cpu().numpy()
+    assert np.array_equal(nout, ref["nout"])
+    m = np.minimum(ref["nout"], pout)
+    valid = np.arange(pout)[None, :] < m[:, None]
+    assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < TOL_FUSED
+    np.testing.assert_allclose(out[valid][:, :, 3], ref["kscores"][valid], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(ps[valid], ref["pscores"][valid], rtol=2e-5, atol=1e-7)
+    assert not out[~valid].any()
+
+
+def test_fused_without_counts_and_host_path(torch_cuda):
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(4)
+    d = synth.make_frames(rig, 257, 2, 133, seed=3)
+    prm = synth.MULTI_PARAMS
+    ref = c_oracle.fused(d["kpts"], d["scores"], None, rig.K, rig.R, rig.t, prm, Pout=4)
+    eng = _engine(rig, prm)
+    res = eng.run_host(d["kpts"], d["scores"], None, Pout=4)
+    assert np.array_equal(res["nout"], ref["nout"])
+    assert rel_l2(res["out"][..., :3], ref["points"]) < TOL_FUSED
+    assert eng.launch_count == 1
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_fused_f32_mode_within_north_star(torch_cuda, case):
+    torch = torch_cuda
+    from oracle import c_oracle
+    rname, F, P, J, prm, pout, kw = CASES[case]
+    rig = _rig(rname)
+    d = synth.make_frames(rig, F, P, J, seed=200 + case, **kw)
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    eng = _engine(rig, prm, precision="f32")
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    res = eng.run(kp, sc, cn, Pout=pout)
+    torch.cuda.synchronize()
+    out, nout = res["out"].cpu().numpy(), res["nout"].cpu().numpy()
+    assert np.array_equal(nout, ref["nout"])
+    m = np.minimum(ref["nout"], pout)
+    valid = np.arange(pout)[None, :] < m[:, None]
+    assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < TOL_NORTH_STAR
+
+
+def test_fused_equals_candidates_then_condense(torch_cuda):
+    """K1 -> K2 composition must reproduce the fused kernel."""
+    torch = torch_cuda
+    rig = synth.ring_rig(5)
+    d = synth.make_frames(rig, 40, 3, 33, seed=9, low_score_frac=0.1, drop_prob=0.1)
+    prm = synth.MULTI_PARAMS
+    eng = _engine(rig, prm)
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    fused = eng.run(kp, sc, cn, Pout=8)
+    c = eng.candidates(kp, sc, cn)
+    torch.cuda.synchronize()
+    keep = c["keep"].cpu().numpy().astype(bool)
+    cand = c["cand"].cpu().numpy()
+    F, N = keep.shape
+    packed = np.zeros_like(cand)
+    ncand = keep.sum(1).astype(np.int32)
+    for f in range(F):
+        packed[f, :ncand[f]] = cand[f][keep[f]]
+    dc, dn = _to_dev(torch, packed, ncand)
+    con = eng.condense(dc, dn, Pout=8)
+    torch.cuda.synchronize()
+    assert np.array_equal(con["nout"].cpu().numpy(), fused["nout"].cpu().numpy())
+    assert rel_l2(fused["out"].cpu().numpy(), con["out"].cpu().numpy()) < TOL_FUSED
+
+
+def test_skew_ray_solver(torch_cuda):
+    import snowmocap_b200 as sv
+    from oracle import c_oracle
+    dist, W = sv.Skew_Ray_Solver(np.array([[1.0], [0], [0]]), np.array([[0], [1.0], [0]]),
+                                 np.array([[-1.0], [0], [0]]), np.array([[0], [-1.0], [2.0]]))
+    assert abs(dist - 2.0) < 1e-13 and np.allclose(W, [0, 0, 1.0], atol=1e-13)
+    rng = np.random.default_rng(0)
+    hm, hs, tm, ts = (rng.standard_normal((1000, 3)) for _ in range(4))
+    eng = sv.triangulation._util_engine()
+    torch = torch_cuda
+    d, m = eng.skew_ray(*_to_dev(torch, hm, hs, tm, ts))
+    d0, m0 = c_oracle.skew_ray(hm, hs, tm, ts)
+    np.testing.assert_allclose(d.cpu().numpy(), d0, rtol=1e-9)
+    np.testing.assert_allclose(m.cpu().numpy(), m0, rtol=1e-9, atol=1e-9)
+
+
+def test_error_behaviour(torch_cuda):
+    import snowmocap_b200 as sv
+    from snowmocap_b200._lib import SnowtriError
+    torch = torch_cuda
+    rig = synth.ring_rig(3)
+    d = synth.make_frames(rig, 2, 1, 17, seed=1)
+    eng = _engine(rig, dict(synth.DEFAULT_PARAMS, center=40))
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    with pytest.raises(SnowtriError):
+        eng.run(kp, sc, cn)                      # centre joint >= J: the reference raises IndexError
+    eng.set_params(center=0)
+    with pytest.raises(SnowtriError):
+        eng.run(kp, sc, cn, keypoint_num=18)     # keypoint_num > J
+    tri = {"hrnet_triangulate_points": [np.zeros((17, 3))] * 3,
+           "hrnet_triangulate_keypoint_scores": [np.ones(17)] * 3, "hrnet_triangulate_person_scores": [1.0] * 3}
+    with pytest.raises(IndexError):
+        sv.Human_Triangulation_Condense(tri, keypoint_num=30)
