@@ -1,0 +1,42 @@
+"""Frame sharding across the GPUs of one box: frames are independent, so each
+rank triangulates a contiguous block of frames with no data-path collective; an optional final
+all-gather collects the dense 3D-joint block on every rank (NCCL over NVLink on GPUs, gloo in
+the CPU tests of the host logic)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(F, rank, world):
+    """Contiguous frame block [lo, hi) of ``rank``; the first F % world ranks get one extra frame."""
+    base, extra = divmod(F, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def all_gather_frames(local, F, group=None):
+    """All-gather per-rank frame blocks (uneven allowed) into the full (F, ...) tensor on every rank."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(F, r, world)[1] - shard_range(F, r, world)[0] for r in range(world)]
+    assert local.shape[0] == sizes[rank], (local.shape, sizes, rank)
+    if len(set(sizes)) == 1:
+        out = torch.empty((F,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[:local.shape[0]] = local
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf, group=group)
+    return torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+
+
+def triangulate_sharded(engine, kpts_local, scores_local, counts_local, F, Pout=None, keypoint_num=None,
+                        gather=True, group=None):
+    """Run the fused path on this rank's frame block; optionally all-gather (out, pscores, nout)."""
+    res = engine.run(kpts_local, scores_local, counts_local, Pout=Pout, keypoint_num=keypoint_num)
+    if not gather or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return res
+    return {k: all_gather_frames(v, F, group) for k, v in res.items()}

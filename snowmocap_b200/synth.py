@@ -109,3 +109,35 @@ def _make_chunk(rig, chunk, P, J, seed, noise_px, low_score_frac, drop_prob, shu
 
 DEFAULT_PARAMS = dict(kst=0.5, ast=0.0, dthr=0.05, cond_tol=10.0, num_tol=0, score_tol=0.0, center=0)
 MULTI_PARAMS = dict(kst=0.5, ast=0.2, dthr=0.05, cond_tol=0.3, num_tol=0, score_tol=0.0, center=0)
+
+
+def make_frames_torch(rig, F, P, J, seed=1234, device="cuda", noise_px=0.5, chunk=8192):
+    """Same distribution as ``make_frames`` generated on the device with torch (benchmark inputs only;
+    not bit-identical to the NumPy generator).  Returns (kpts (F,C,P,J,2) f32, scores (F,C,P,J) f32)."""
+    import torch
+    C = rig.C
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    Rt = torch.as_tensor(rig.R, device=device).transpose(1, 2).contiguous()      # world->camera
+    K = torch.as_tensor(rig.K, device=device)
+    t = torch.as_tensor(rig.t, device=device)
+    kpts = torch.empty((F, C, P, J, 2), dtype=torch.float32, device=device)
+    scores = torch.empty((F, C, P, J), dtype=torch.float32, device=device)
+    for f0 in range(0, F, chunk):
+        n = min(chunk, F - f0)
+        centre = torch.zeros((n, P, 1, 3), dtype=torch.float64, device=device)
+        centre[..., :2] = torch.rand((n, P, 1, 2), generator=gen, dtype=torch.float64, device=device) * 4 - 2
+        body = torch.rand((n, P, J, 3), generator=gen, dtype=torch.float64, device=device)
+        body[..., :2] = body[..., :2] * 0.8 - 0.4
+        body[..., 2] *= 1.8
+        X = centre + body                                                           # (n,P,J,3)
+        Xc = torch.einsum("cij,ncpqj->ncpqi", Rt, X[:, None] - t[None, :, None, None, :])
+        uvw = torch.einsum("cij,ncpqj->ncpqi", K, Xc)
+        uv = uvw[..., :2] / uvw[..., 2:3]
+        uv = uv + noise_px * torch.randn(uv.shape, generator=gen, dtype=torch.float64, device=device)
+        # independent person order per camera, like a detector (main.py:54)
+        perm = torch.argsort(torch.rand((n, C, P), generator=gen, device=device), dim=-1)
+        uv = torch.gather(uv, 2, perm[..., None, None].expand(-1, -1, -1, J, 2))
+        kpts[f0:f0 + n] = uv.to(torch.float32)
+        scores[f0:f0 + n] = torch.rand((n, C, P, J), generator=gen, device=device) * 0.4 + 0.6
+    return kpts, scores
