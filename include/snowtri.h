@@ -59,8 +59,9 @@ int snowtri_destroy(snowtri_t* h);
 int snowtri_set_params(snowtri_t* h, double kst, double ast, double dthr,
                        double cond_tol, int num_tol, double score_tol, int center);
 int snowtri_set_precision(snowtri_t* h, int precision);
-/* Launch tuning for tests/benchmarks: frames staged per CTA iteration and CTA cap (0 = automatic). */
-int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas);
+/* Launch tuning for tests/benchmarks: frames staged per CTA iteration, CTA cap, block size
+ * (256 or 512); 0 = automatic. */
+int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads);
 
 /* Fused hot path for a batch of F frames: rays -> all camera-pair x person-pair candidates ->
  * gating -> greedy clustering -> score-weighted fuse (main.py:55-71 for every frame).

@@ -17,7 +17,7 @@ SYMBOLS = {
     "snowtri_destroy": (_I, [_P]),
     "snowtri_set_params": (_I, [_P, _D, _D, _D, _D, _I, _D, _I]),
     "snowtri_set_precision": (_I, [_P, _I]),
-    "snowtri_set_tuning": (_I, [_P, _I, _I]),
+    "snowtri_set_tuning": (_I, [_P, _I, _I, _I]),
     "snowtri_run": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "snowtri_run_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "snowtri_candidates": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

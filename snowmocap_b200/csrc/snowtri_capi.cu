@@ -15,9 +15,11 @@ using namespace snowtri;
 struct snowtri_handle {
     int device, C, sm_count, max_smem;
     double* d_cam;  // (C,12) M = R*inv(K), t
+    double* cam_host;
+    int smem_per_sm;
     Params prm;
     int precision;
-    int tune_G, tune_ctas;
+    int tune_G, tune_ctas, tune_threads;
     long long launches;
     int last_grid, last_block, last_smem, last_G;
     // device staging owned by the handle (snowtri_run_host only)
@@ -92,6 +94,7 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
     }
     h->sm_count = prop.multiProcessorCount;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
+    h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     double* cam = (double*)malloc(sizeof(double) * 12 * C);
     for (int c = 0; c < C; ++c) {
         double Kinv[9];
@@ -106,14 +109,13 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
     }
     e = cudaMalloc(&h->d_cam, sizeof(double) * 12 * C);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_cam, cam, sizeof(double) * 12 * C, cudaMemcpyHostToDevice);
-    free(cam);
+    h->cam_host = cam;
     if (e != cudaSuccess) {
         if (h->d_cam) cudaFree(h->d_cam);
+        free(cam);
         free(h);
         return fail(nullptr, SNOWTRI_E_CUDA, "snowtri_create: %s", cudaGetErrorString(e));
     }
-    cudaFuncSetAttribute(fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
-    cudaFuncSetAttribute(fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
     cudaFuncSetAttribute(condense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->max_smem);
     *out = h;
     return SNOWTRI_OK;
@@ -125,6 +127,7 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     for (int i = 0; i < 6; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->d_cam) cudaFree(h->d_cam);
+    free(h->cam_host);
     free(h);
     return SNOWTRI_OK;
 }
@@ -149,10 +152,13 @@ extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
     return SNOWTRI_OK;
 }
 
-extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas) {
+extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_tuning: NULL handle");
+    if (threads != 0 && threads != 256 && threads != 512)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_set_tuning: threads must be 0 (auto), 256 or 512");
     h->tune_G = frames_per_group > 0 ? frames_per_group : 0;
     h->tune_ctas = max_ctas > 0 ? max_ctas : 0;
+    h->tune_threads = threads;
     return SNOWTRI_OK;
 }
 
@@ -192,14 +198,121 @@ static size_t fused_layout(int C, int P, int J, int Jout, int Pout, int G, size_
     L->ab = take(G * ncand, 4);
     L->klist = take(G * ncand * 4, 4);
     L->memb = take(G * ncand * 4, 4);
+    L->membp = take(G * ncand * 4, 4);
     L->cstart = take(G * ncand * 4, 4);
     L->cn = take(G * ncand * 4, 4);
     L->ksum = take(G * ncand * 8, 8);
     L->slot = take(G * ncand * 4, 4);
     L->kcount = take((size_t)G * 2 * 4, 4);
     L->ks = take((size_t)G * Pout * Jout * tsz, 16);
+    L->cobs = take((size_t)G * Pout * kCliqueMax, 4);
+    L->clq = take((size_t)G * Pout, 4);
     L->total = (int)o;
     return o;
+}
+
+template <typename T, int NT, int CM, int NCH>
+static cudaError_t launch_fused(const FusedArgs<T>& a, int grid, cudaStream_t st) {
+    auto kern = fused_kernel<T, NT, CM, NCH>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.sm.total);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, NT, a.sm.total, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <typename T, int NT, int CM>
+static cudaError_t launch_fused_nch(const FusedArgs<T>& a, int nch, int grid, cudaStream_t st) {
+    switch (nch) {
+        case 1: return launch_fused<T, NT, CM, 1>(a, grid, st);
+        case 5: return launch_fused<T, NT, CM, 5>(a, grid, st);
+        default: return launch_fused<T, NT, CM, 0>(a, grid, st);
+    }
+}
+
+template <typename T, int NT>
+static cudaError_t launch_fused_cm(const FusedArgs<T>& a, int cm, int nch, int grid, cudaStream_t st) {
+    switch (cm) {
+        case 4: return launch_fused_nch<T, NT, 4>(a, nch, grid, st);
+        case 8: return launch_fused_nch<T, NT, 8>(a, nch, grid, st);
+        default: return launch_fused_nch<T, NT, 0>(a, nch, grid, st);
+    }
+}
+
+template <typename T>
+static int run_fused(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int P,
+                     int J, int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream) {
+    const int C = h->C;
+    const size_t tsz = sizeof(T);
+    FusedArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
+    a.out = d_out; a.pscores = d_pscores; a.nout = d_nout; a.cam = h->d_cam;
+    a.F = F; a.C = C; a.P = P; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
+    a.npairs = C * (C - 1) / 2;
+    a.ncand = a.npairs * P * P;
+    a.R = C * P * J;
+    a.prm = h->prm;
+    a.all_kept = (h->prm.ast <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
+    a.never_filter = (h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
+
+    // template selection
+    const int cm = C <= 4 ? 4 : (C <= kCliqueMax ? 8 : 0);
+    const int nch = J <= 32 ? 1 : (J <= 160 ? 5 : 0);
+    for (int x = 0; x < cm - 1 && x < C; ++x)
+        for (int y = x + 1; y < cm && y < C; ++y) {
+            const int e = (x * cm - x * (x + 1) / 2 + y - x - 1) * 6;
+            for (int k = 0; k < 3; ++k) {
+                a.pdc[e + k] = (T)(h->cam_host[12 * y + 9 + k] - h->cam_host[12 * x + 9 + k]);
+                a.pdc[e + 3 + k] = (T)((h->cam_host[12 * x + 9 + k] + h->cam_host[12 * y + 9 + k]) / 2);
+            }
+        }
+
+    // frames per group / block size.  256 threads x 2 CTAs per SM when two groups fit in shared
+    // memory side by side (overlaps one CTA's barriers with the other's math), else 512 x 1.
+    auto largest_G = [&](size_t budget, int cap) -> int {
+        for (int g = cap; g >= 1; --g)
+            if ((size_t)g * a.R <= 65535 && fused_layout(C, P, J, a.Jout, Pout, g, tsz, &a.sm) <= budget) return g;
+        return 0;
+    };
+    int cap = h->tune_G > 0 ? h->tune_G : 32;
+    if (cap > F) cap = F;
+    const size_t full = (size_t)h->max_smem, half = ((size_t)h->smem_per_sm - 2048) / 2 - 1024;
+    int nt = h->tune_threads;
+    int G = 0;
+    if (nt == 0) {
+        const int g2 = largest_G(half, cap);
+        if (g2 >= 1 && (size_t)g2 * a.R >= 2048) { nt = 256; G = g2; }
+        else { nt = 512; G = largest_G(full, cap); }
+    } else {
+        G = largest_G(nt == 256 ? half : full, cap);
+        if (G == 0 && nt == 256) G = largest_G(full, cap);
+    }
+    if (G == 0)
+        return fail(h, SNOWTRI_E_UNSUPPORTED,
+                    "snowtri_run: one frame (C=%d P=%d J=%d Pout=%d) needs %zu B of shared memory, device allows %d",
+                    C, P, J, Pout, fused_layout(C, P, J, a.Jout, Pout, 1, tsz, &a.sm), h->max_smem);
+    const int ctas_per_sm = (nt == 256 && fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm) <= half) ? 2 : 1;
+    if (h->tune_G == 0) {
+        // keep a few groups per CTA when the batch is large enough, and prefer (G*R)%4==0 (TMA)
+        while (G > 1 && (F + G - 1) / G < 4 * h->sm_count * ctas_per_sm) --G;
+        for (int g = G; g >= 1 && g > G - 4; --g)
+            if (((size_t)g * a.R) % 4 == 0) { G = g; break; }
+    }
+    fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm);
+    a.G = G;
+    const bool aligned = (((uintptr_t)d_kpts & 15u) == 0) && (((uintptr_t)d_scores & 15u) == 0);
+    a.use_tma = (aligned && ((size_t)G * a.R) % 4 == 0) ? 1 : 0;
+
+    const int ngroups = (F + G - 1) / G;
+    int grid = h->sm_count * ctas_per_sm;
+    if (grid > ngroups) grid = ngroups;
+    if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = nt == 256 ? launch_fused_cm<T, 256>(a, cm, nch, grid, st) : launch_fused_cm<T, 512>(a, cm, nch, grid, st);
+    if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "fused_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    h->last_grid = grid; h->last_block = nt; h->last_smem = a.sm.total; h->last_G = G;
+    return SNOWTRI_OK;
 }
 
 extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F,
@@ -220,53 +333,10 @@ extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_sco
     if (((uintptr_t)d_kpts & 7u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_run: d_kpts must be 8-byte aligned");
     CUDA_TRY(h, cudaSetDevice(h->device));
 
-    const int C = h->C;
-    const size_t tsz = h->precision == SNOWTRI_PREC_F32 ? 4 : 8;
-    FusedArgs a;
-    memset(&a, 0, sizeof(a));
-    a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
-    a.out = d_out; a.pscores = d_pscores; a.nout = d_nout; a.cam = h->d_cam;
-    a.F = F; a.C = C; a.P = P; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
-    a.npairs = C * (C - 1) / 2;
-    a.ncand = a.npairs * P * P;
-    a.R = C * P * J;
-    a.prm = h->prm;
-    a.all_kept = (h->prm.ast <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
-    a.never_filter = (h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
-
-    // frames per group: as many as fit in shared memory (<= 32), preferring TMA-aligned groups
-    int Gmax = h->tune_G > 0 ? h->tune_G : 32;
-    if (Gmax > F) Gmax = F;
-    int G = 0;
-    for (int g = Gmax; g >= 1; --g)
-        if (fused_layout(C, P, J, a.Jout, Pout, g, tsz, &a.sm) <= (size_t)h->max_smem) { G = g; break; }
-    if (G == 0)
-        return fail(h, SNOWTRI_E_UNSUPPORTED,
-                    "snowtri_run: one frame (C=%d P=%d J=%d Pout=%d) needs %zu B of shared memory, device allows %d",
-                    C, P, J, Pout, fused_layout(C, P, J, a.Jout, Pout, 1, tsz, &a.sm), h->max_smem);
-    if (h->tune_G == 0) {
-        // keep at least ~4 groups per SM when the batch is large enough, and prefer (G*R)%4==0
-        while (G > 1 && (F + G - 1) / G < 4 * h->sm_count) --G;
-        for (int g = G; g >= 1 && g > G - 4; --g)
-            if (((size_t)g * a.R) % 4 == 0) { G = g; break; }
-    }
-    fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm);
-    a.G = G;
-    const bool aligned = (((uintptr_t)d_kpts & 15u) == 0) && (((uintptr_t)d_scores & 15u) == 0);
-    a.use_tma = (aligned && ((size_t)G * a.R) % 4 == 0) ? 1 : 0;
-
-    const int ngroups = (F + G - 1) / G;
-    int grid = ngroups < h->sm_count ? ngroups : h->sm_count;
-    if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (h->precision == SNOWTRI_PREC_F32)
-        fused_kernel<float><<<grid, kThreads, a.sm.total, st>>>(a);
-    else
-        fused_kernel<double><<<grid, kThreads, a.sm.total, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
-    h->launches += 1;
-    h->last_grid = grid; h->last_block = kThreads; h->last_smem = a.sm.total; h->last_G = G;
-    return SNOWTRI_OK;
+    const int rc = h->precision == SNOWTRI_PREC_F32
+                       ? run_fused<float>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream)
+                       : run_fused<double>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+    return rc;
 }
 
 static int ensure_stage(snowtri_t* h, int i, size_t bytes) {

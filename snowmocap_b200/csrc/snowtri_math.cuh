@@ -77,6 +77,21 @@ __device__ __forceinline__ PairSol<T> pair_solve(const V3<T>& hm, const V3<T>& h
     return s;
 }
 
+// Same with the squared norms A = hm.hm and Cc = hs.hs supplied by the caller (reused rays).
+template <typename T>
+__device__ __forceinline__ PairSol<T> pair_solve_a(const V3<T>& hm, T A, const V3<T>& hs, T Cc, const V3<T>& d) {
+    const T B = dot3(hm, hs), D = dot3(hm, d), E = dot3(hs, d);
+    PairSol<T> s;
+    s.det = fma(A, Cc, -(B * B));
+    s.n0 = fma(Cc, D, -(B * E));
+    s.n1 = fma(A, E, -(B * D));
+    const T qx = fma(hm.x, s.n0, fma(hs.x, s.n1, -(d.x * s.det)));
+    const T qy = fma(hm.y, s.n0, fma(hs.y, s.n1, -(d.y * s.det)));
+    const T qz = fma(hm.z, s.n0, fma(hs.z, s.n1, -(d.z * s.det)));
+    s.qq = fma(qx, qx, fma(qy, qy, qz * qz));
+    return s;
+}
+
 // g = gated (sm+ss)*0.00025*rsqrt(q.q); the reference's score is 2*g*det.
 template <typename T>
 __device__ __forceinline__ T gated_g(const PairSol<T>& s, float sm, float ss, float kst_f, T dthr) {
@@ -108,6 +123,21 @@ __device__ __forceinline__ V3<T> pair_midpoint(const PairSol<T>& s, const V3<T>&
     w.y = fma(v.y, h, mid.y);
     w.z = fma(v.z, h, mid.z);
     return w;
+}
+
+// End of the per-joint fuse (reference triangulation.py:142-148): S = sum of member scores,
+// (X,Y,Z) = sum of score*point.  Returns the keypoint score S/n; a zero S leaves (0,0,0), 0 (Q6/Q7).
+template <typename T>
+__device__ __forceinline__ T finish_joint(T S, int n, T& X, T& Y, T& Z) {
+    if (S == (T)0) {
+        X = Y = Z = (T)0;
+        return (T)0;
+    }
+    const T rS = rcp_t(S);
+    X *= rS;
+    Y *= rS;
+    Z *= rS;
+    return S * rcp_t((T)n);
 }
 
 // Back-projection f = (R K^-1) [u v 1]^T (reference snowvision/camera.py:240-244); M row-major 3x3.

@@ -73,8 +73,8 @@ class TriangulationEngine:
         _lib.check(self._lib.snowtri_set_precision(self._h, code), self._h)
         self.precision = precision
 
-    def set_tuning(self, frames_per_group=0, max_ctas=0):
-        _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas)), self._h)
+    def set_tuning(self, frames_per_group=0, max_ctas=0, threads=0):
+        _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas), int(threads)), self._h)
 
     @property
     def launch_count(self):
