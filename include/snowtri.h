@@ -60,7 +60,7 @@ int snowtri_set_params(snowtri_t* h, double kst, double ast, double dthr,
                        double cond_tol, int num_tol, double score_tol, int center);
 int snowtri_set_precision(snowtri_t* h, int precision);
 /* Launch tuning for tests/benchmarks: frames staged per CTA iteration, CTA cap, block size
- * (256 or 512); 0 = automatic. */
+ * (256 or 512; -256 = 256 threads with stored rays even for one person per camera); 0 = automatic. */
 int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads);
 
 /* Fused hot path for a batch of F frames: rays -> all camera-pair x person-pair candidates ->

@@ -19,7 +19,7 @@ struct snowtri_handle {
     int smem_per_sm;
     Params prm;
     int precision;
-    int tune_G, tune_ctas, tune_threads;
+    int tune_G, tune_ctas, tune_threads, no_fly, last_fly;
     long long launches;
     int last_grid, last_block, last_smem, last_G;
     // device staging owned by the handle (snowtri_run_host only)
@@ -154,11 +154,12 @@ extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
 
 extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_tuning: NULL handle");
-    if (threads != 0 && threads != 256 && threads != 512)
-        return fail(h, SNOWTRI_E_ARG, "snowtri_set_tuning: threads must be 0 (auto), 256 or 512");
+    if (threads != 0 && threads != 256 && threads != 512 && threads != -256)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_set_tuning: threads must be 0 (auto), 256, 512 or -256");
     h->tune_G = frames_per_group > 0 ? frames_per_group : 0;
     h->tune_ctas = max_ctas > 0 ? max_ctas : 0;
-    h->tune_threads = threads;
+    h->no_fly = threads == -256 ? 1 : 0;   /* -256: 256 threads with stored rays even when P == 1 */
+    h->tune_threads = threads == -256 ? 256 : threads;
     return SNOWTRI_OK;
 }
 
@@ -174,24 +175,32 @@ extern "C" int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int
 }
 
 // Shared-memory layout of fused_kernel for G frames per group; returns total bytes.
-static size_t fused_layout(int C, int P, int J, int Jout, int Pout, int G, size_t tsz, FusedSmem* L) {
+// fly: rays are not stored, the (u,v,score) staging is double-buffered instead.
+static size_t fused_layout(int C, int P, int J, int Jout, int Pout, int G, size_t tsz, bool fly, int nthreads,
+                           FusedSmem* L) {
     const size_t npairs = (size_t)C * (C - 1) / 2, ncand = npairs * P * P, R = (size_t)C * P * J;
-    size_t o = 16;  // mbarrier
+    size_t o = 16;  // two mbarriers
     auto take = [&](size_t bytes, size_t align) -> int {
         o = (o + align - 1) / align * align;
         const size_t r = o;
         o += bytes;
         return (int)r;
     };
+    memset(L, 0, sizeof(*L));
     L->cam = take((size_t)C * 9 * tsz, 16);
     L->pairs = take(npairs * 2, 4);
     L->pd = take(npairs * 6 * tsz, 16);
-    L->stage_uv = take(G * R * 8, 128);
-    L->stage_s = take(G * R * 4, 128);
-    L->hx = take(G * R * tsz, 16);
-    L->hy = take(G * R * tsz, 16);
-    L->hz = take(G * R * tsz, 16);
-    L->sc = take(G * R * 4, 16);
+    const size_t uvb = (G * R * 8 + 127) / 128 * 128, sb = (G * R * 4 + 127) / 128 * 128;
+    L->stage_uv = take(uvb * (fly ? 2 : 1), 128);
+    L->stage_s = take(sb * (fly ? 2 : 1), 128);
+    L->stage_stride_uv = fly ? (int)uvb : 0;
+    L->stage_stride_s = fly ? (int)sb : 0;
+    if (!fly) {
+        L->hx = take(G * R * tsz, 16);
+        L->hy = take(G * R * tsz, 16);
+        L->hz = take(G * R * tsz, 16);
+        L->sc = take(G * R * 4, 16);
+    }
     L->cnt = take((size_t)G * C * 4, 4);
     L->cen = take(G * ncand * 24, 8);
     L->keep = take(G * ncand, 4);
@@ -207,34 +216,42 @@ static size_t fused_layout(int C, int P, int J, int Jout, int Pout, int G, size_
     L->ks = take((size_t)G * Pout * Jout * tsz, 16);
     L->cobs = take((size_t)G * Pout * kCliqueMax, 4);
     L->clq = take((size_t)G * Pout, 4);
+    L->wtmp = take((size_t)(2 * (nthreads / 32) + 4) * 4, 4);
     L->total = (int)o;
     return o;
 }
 
-template <typename T, int NT, int CM, int NCH>
+template <typename T, int NT, int CM, int NCH, bool FLY>
 static cudaError_t launch_fused(const FusedArgs<T>& a, int grid, cudaStream_t st) {
-    auto kern = fused_kernel<T, NT, CM, NCH>;
+    auto kern = fused_kernel<T, NT, CM, NCH, FLY>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, a.sm.total);
     if (e != cudaSuccess) return e;
     kern<<<grid, NT, a.sm.total, st>>>(a);
     return cudaGetLastError();
 }
 
-template <typename T, int NT, int CM>
+template <typename T, int NT, int CM, bool FLY>
 static cudaError_t launch_fused_nch(const FusedArgs<T>& a, int nch, int grid, cudaStream_t st) {
-    switch (nch) {
-        case 1: return launch_fused<T, NT, CM, 1>(a, grid, st);
-        case 5: return launch_fused<T, NT, CM, 5>(a, grid, st);
-        default: return launch_fused<T, NT, CM, 0>(a, grid, st);
-    }
+    return nch == 5 ? launch_fused<T, NT, CM, 5, FLY>(a, grid, st) : launch_fused<T, NT, CM, 0, FLY>(a, grid, st);
 }
 
-template <typename T, int NT>
-static cudaError_t launch_fused_cm(const FusedArgs<T>& a, int cm, int nch, int grid, cudaStream_t st) {
+template <typename T>
+static cudaError_t launch_fused_any(const FusedArgs<T>& a, int nt, int cm, int nch, bool fly, int grid, cudaStream_t st) {
+    if (fly) {  // fly mode exists for 256 threads and the <= 8-camera tables only
+        return cm == 4 ? launch_fused_nch<T, 256, 4, true>(a, nch, grid, st)
+                       : launch_fused_nch<T, 256, 8, true>(a, nch, grid, st);
+    }
+    if (nt == 256) {
+        switch (cm) {
+            case 4: return launch_fused_nch<T, 256, 4, false>(a, nch, grid, st);
+            case 8: return launch_fused_nch<T, 256, 8, false>(a, nch, grid, st);
+            default: return launch_fused_nch<T, 256, 0, false>(a, nch, grid, st);
+        }
+    }
     switch (cm) {
-        case 4: return launch_fused_nch<T, NT, 4>(a, nch, grid, st);
-        case 8: return launch_fused_nch<T, NT, 8>(a, nch, grid, st);
-        default: return launch_fused_nch<T, NT, 0>(a, nch, grid, st);
+        case 4: return launch_fused_nch<T, 512, 4, false>(a, nch, grid, st);
+        case 8: return launch_fused_nch<T, 512, 8, false>(a, nch, grid, st);
+        default: return launch_fused_nch<T, 512, 0, false>(a, nch, grid, st);
     }
 }
 
@@ -254,10 +271,12 @@ static int run_fused(snowtri_t* h, const float* d_kpts, const float* d_scores, c
     a.prm = h->prm;
     a.all_kept = (h->prm.ast <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
     a.never_filter = (h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0) ? 1 : 0;
+    a.inv_dthr = h->prm.dthr > 0.0 ? (T)(1.0 / h->prm.dthr) : (T)INFINITY;
+    a.tol2 = h->prm.cond_tol >= 0.0 ? h->prm.cond_tol * h->prm.cond_tol : -1.0;
 
     // template selection
     const int cm = C <= 4 ? 4 : (C <= kCliqueMax ? 8 : 0);
-    const int nch = J <= 32 ? 1 : (J <= 160 ? 5 : 0);
+    const int nch = (J > 32 && J <= 160) ? 5 : 0;
     for (int x = 0; x < cm - 1 && x < C; ++x)
         for (int y = x + 1; y < cm && y < C; ++y) {
             const int e = (x * cm - x * (x + 1) / 2 + y - x - 1) * 6;
@@ -266,39 +285,52 @@ static int run_fused(snowtri_t* h, const float* d_kpts, const float* d_scores, c
                 a.pdc[e + 3 + k] = (T)((h->cam_host[12 * x + 9 + k] + h->cam_host[12 * y + 9 + k]) / 2);
             }
         }
+    for (int c = 0; c < C && c < kCliqueMax; ++c)
+        for (int k = 0; k < 9; ++k) a.camc[9 * c + k] = (T)h->cam_host[12 * c + k];
 
-    // frames per group / block size.  256 threads x 2 CTAs per SM when two groups fit in shared
-    // memory side by side (overlaps one CTA's barriers with the other's math), else 512 x 1.
-    auto largest_G = [&](size_t budget, int cap) -> int {
-        for (int g = cap; g >= 1; --g)
-            if ((size_t)g * a.R <= 65535 && fused_layout(C, P, J, a.Jout, Pout, g, tsz, &a.sm) <= budget) return g;
-        return 0;
-    };
+    // Block size / frames per group.  256 threads x 2 CTAs per SM when two groups fit in shared
+    // memory side by side (one CTA's barriers overlap the other's math), else 512 x 1.  With one
+    // person per camera (and <= 8 cameras) rays are recomputed on the fly instead of stored.
+    const size_t full = (size_t)h->max_smem, half = ((size_t)h->smem_per_sm - 2048) / 2 - 1024;
     int cap = h->tune_G > 0 ? h->tune_G : 32;
     if (cap > F) cap = F;
-    const size_t full = (size_t)h->max_smem, half = ((size_t)h->smem_per_sm - 2048) / 2 - 1024;
-    int nt = h->tune_threads;
-    int G = 0;
-    if (nt == 0) {
-        const int g2 = largest_G(half, cap);
-        if (g2 >= 1 && (size_t)g2 * a.R >= 2048) { nt = 256; G = g2; }
-        else { nt = 512; G = largest_G(full, cap); }
-    } else {
-        G = largest_G(nt == 256 ? half : full, cap);
-        if (G == 0 && nt == 256) G = largest_G(full, cap);
+    auto largest_G = [&](size_t budget, int cap_, bool fly, int nt_) -> int {
+        for (int g = cap_; g >= 1; --g)
+            if ((size_t)g * a.R <= 65535 && fused_layout(C, P, J, a.Jout, Pout, g, tsz, fly, nt_, &a.sm) <= budget) return g;
+        return 0;
+    };
+    bool fly = (P == 1 && cm > 0 && h->tune_threads != 512 && !h->no_fly);
+    int nt = h->tune_threads, G = 0;
+    if (fly) {
+        G = largest_G(half, cap, true, 256);
+        if (G == 0) fly = false;
+        else nt = 256;
+    }
+    if (!fly) {
+        if (nt == 0) {
+            const int g2 = largest_G(half, cap, false, 256);
+            if (g2 >= 1 && (size_t)g2 * a.R >= 2048) { nt = 256; G = g2; }
+            else { nt = 512; G = largest_G(full, cap, false, 512); }
+        } else {
+            G = largest_G(nt == 256 ? half : full, cap, false, nt);
+            if (G == 0 && nt == 256) G = largest_G(full, cap, false, nt);
+        }
     }
     if (G == 0)
         return fail(h, SNOWTRI_E_UNSUPPORTED,
                     "snowtri_run: one frame (C=%d P=%d J=%d Pout=%d) needs %zu B of shared memory, device allows %d",
-                    C, P, J, Pout, fused_layout(C, P, J, a.Jout, Pout, 1, tsz, &a.sm), h->max_smem);
-    const int ctas_per_sm = (nt == 256 && fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm) <= half) ? 2 : 1;
+                    C, P, J, Pout, fused_layout(C, P, J, a.Jout, Pout, 1, tsz, false, 512, &a.sm), h->max_smem);
+    const int ctas_per_sm = (nt == 256 && fused_layout(C, P, J, a.Jout, Pout, G, tsz, fly, nt, &a.sm) <= half) ? 2 : 1;
     if (h->tune_G == 0) {
-        // keep a few groups per CTA when the batch is large enough, and prefer (G*R)%4==0 (TMA)
+        // keep a few groups per CTA when the batch is large enough; warp-per-frame phases like
+        // G to be a multiple of the warp count; TMA staging needs (G*R) % 4 == 0
         while (G > 1 && (F + G - 1) / G < 4 * h->sm_count * ctas_per_sm) --G;
+        const int nw = nt / 32;
+        if (a.ncand <= 64 && G > nw) G = G / nw * nw;
         for (int g = G; g >= 1 && g > G - 4; --g)
             if (((size_t)g * a.R) % 4 == 0) { G = g; break; }
     }
-    fused_layout(C, P, J, a.Jout, Pout, G, tsz, &a.sm);
+    fused_layout(C, P, J, a.Jout, Pout, G, tsz, fly, nt, &a.sm);
     a.G = G;
     const bool aligned = (((uintptr_t)d_kpts & 15u) == 0) && (((uintptr_t)d_scores & 15u) == 0);
     a.use_tma = (aligned && ((size_t)G * a.R) % 4 == 0) ? 1 : 0;
@@ -307,11 +339,11 @@ static int run_fused(snowtri_t* h, const float* d_kpts, const float* d_scores, c
     int grid = h->sm_count * ctas_per_sm;
     if (grid > ngroups) grid = ngroups;
     if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
-    cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = nt == 256 ? launch_fused_cm<T, 256>(a, cm, nch, grid, st) : launch_fused_cm<T, 512>(a, cm, nch, grid, st);
+    const cudaError_t e = launch_fused_any<T>(a, nt, cm, nch, fly, grid, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "fused_kernel launch failed: %s", cudaGetErrorString(e));
     h->launches += 1;
     h->last_grid = grid; h->last_block = nt; h->last_smem = a.sm.total; h->last_G = G;
+    h->last_fly = fly ? 1 : 0;
     return SNOWTRI_OK;
 }
 

@@ -152,7 +152,7 @@ def _rig(name):
 
 
 @pytest.mark.parametrize("case", range(len(CASES)))
-@pytest.mark.parametrize("tuning", [(0, 0, 0), (1, 3, 256), (5, 7, 512), (3, 0, 256)])
+@pytest.mark.parametrize("tuning", [(0, 0, 0), (1, 3, 256), (5, 7, 512), (3, 0, -256), (8, 0, 0)])
 def test_fused_matches_c_oracle(torch_cuda, case, tuning):
     """Seeded synthetic batches vs the C oracle, with different frames-per-group / CTA counts
     (exercises the TMA and the plain-load staging paths, group tails and the persistent loop)."""
