@@ -11,6 +11,9 @@ _LAZY = {"TriangulationEngine": "engine", "triangulate_batch": "engine", "Skew_R
          "Human_Triangulation": "triangulation", "Human_Triangulation_Condense": "triangulation"}
 
 
+__all__ = ["Camera", "CameraGroup"] + sorted(_LAZY)   # `from snowmocap_b200 import *` overrides the reference's names
+
+
 def __getattr__(name):
     if name in _LAZY:
         import importlib
