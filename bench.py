@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
-    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32", "mixed"])
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")

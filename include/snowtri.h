@@ -43,7 +43,8 @@ enum {
  * always compute in float64 like the reference. */
 enum {
     SNOWTRI_PREC_F64 = 0,      /* float64 arithmetic throughout (default; matches the reference) */
-    SNOWTRI_PREC_F32 = 1       /* float32 arithmetic, float64 re-evaluation of decisions near a threshold */
+    SNOWTRI_PREC_F32 = 1,      /* float32 arithmetic, float64 re-evaluation of decisions near a threshold */
+    SNOWTRI_PREC_MIXED = 2     /* float32 arithmetic, float64 for the ray-distance numerator and the decisions */
 };
 
 /* Camera parameter container on the device; replaces Camera/CameraGroup's K, R, t
@@ -60,7 +61,10 @@ int snowtri_set_params(snowtri_t* h, double kst, double ast, double dthr,
                        double cond_tol, int num_tol, double score_tol, int center);
 int snowtri_set_precision(snowtri_t* h, int precision);
 /* Launch tuning for tests/benchmarks: frames staged per CTA iteration, CTA cap, block size
- * (256 or 512; -256 = 256 threads with stored rays even for one person per camera); 0 = automatic. */
+ * (256 or 512; -256 = 256 threads with stored rays even for one person per camera); 0 = automatic.
+ * One person per camera with the shipped thresholds (ast <= 0, score_tol <= 0, kst >= 0, C <= 8) runs the
+ * warp-autonomous single-person kernel, where frames_per_group is the frames per warp tile (<= 32);
+ * any non-zero `threads` (-1 = "automatic block size") selects the general fused kernel instead. */
 int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads);
 
 /* Fused hot path for a batch of F frames: rays -> all camera-pair x person-pair candidates ->
@@ -108,6 +112,7 @@ int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */
 int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group);
+const char* snowtri_last_kernel(snowtri_t* h);      /* "p1" (single-person kernel), "fused" or "fused-fly"; "" before any run */
 int snowtri_version(void);
 
 #ifdef __cplusplus

@@ -8,7 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsnowtri.so")
 
 OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
-PREC_F64, PREC_F32 = 0, 1
+PREC_F64, PREC_F32, PREC_MIXED = 0, 1, 2
 
 # Every symbol include/snowtri.h declares: name -> (restype, argtypes)
 _P, _I, _D = ct.c_void_p, ct.c_int, ct.c_double
@@ -26,6 +26,7 @@ SYMBOLS = {
     "snowtri_last_error": (ct.c_char_p, [_P]),
     "snowtri_launch_count": (ct.c_longlong, [_P]),
     "snowtri_last_launch_info": (_I, [_P, ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I)]),
+    "snowtri_last_kernel": (ct.c_char_p, [_P]),
     "snowtri_version": (_I, []),
 }
 

@@ -4,13 +4,19 @@ from __future__ import annotations
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsnowtri.so")
-SOURCES = [os.path.join(PKG, "csrc", "snowtri_capi.cu")]
-HEADERS = [os.path.join(PKG, "csrc", "snowtri_kernels.cuh"), os.path.join(PKG, "csrc", "snowtri_math.cuh"),
-           os.path.join(ROOT, "include", "snowtri.h")]
+OBJ_DIR = os.path.join(PKG, "build")
+SOURCES = [os.path.join(CSRC, "snowtri_capi.cu"), os.path.join(CSRC, "snowtri_p1.cu")]
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h"))] + \
+           [os.path.join(ROOT, "include", "snowtri.h")]
 
 
 def nvcc_path():
@@ -24,21 +30,43 @@ def up_to_date():
     if not os.path.exists(LIB):
         return False
     t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(p) <= t for p in SOURCES + HEADERS)
+    return all(os.path.getmtime(p) <= t for p in SOURCES + _headers())
 
 
-def build(force=False, verbose=False):
-    """Compile snowmocap_b200/libsnowtri.so for sm_100a (cross-compiles without a GPU)."""
-    if not force and up_to_date():
-        return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(PKG, "csrc"),
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + SOURCES
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
+def _flags(verbose):
+    fl = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+          "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-Xcompiler", "-fPIC"]
     # $CC/$CXX in this image point at a wrapper nvcc does not need; use the system g++
     if os.path.exists("/usr/bin/g++"):
-        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
-    subprocess.run(cmd, check=True, env=env)
+        fl = ["-ccbin", "/usr/bin/g++"] + fl
+    if verbose:
+        fl.append("-Xptxas=-v")
+    return fl
+
+
+def build(force=False, verbose=False, only=None):
+    """Compile snowmocap_b200/libsnowtri.so for sm_100a (cross-compiles without a GPU).
+
+    One object per translation unit, compiled in parallel, then one shared-library link."""
+    if not force and only is None and up_to_date():
+        return LIB
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc, hdr_t = nvcc_path(), max(os.path.getmtime(p) for p in _headers())
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        stale = force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr_t)
+        if only is not None:
+            stale = os.path.basename(src) in only or not os.path.exists(obj)
+        if stale:
+            r = subprocess.run([nvcc] + _flags(verbose) + ["-c", src, "-o", obj], capture_output=True, text=True)
+            if verbose or r.returncode:
+                print(r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError(f"nvcc failed on {src}")
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.run([nvcc] + _flags(False) + ["-shared", "-o", LIB] + objs, check=True)
     return LIB

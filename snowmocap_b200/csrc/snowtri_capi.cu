@@ -8,44 +8,13 @@
 #include <string.h>
 
 #include "snowtri.h"
+#include "snowtri_internal.h"
 #include "snowtri_kernels.cuh"
 
 using namespace snowtri;
 
-struct snowtri_handle {
-    int device, C, sm_count, max_smem;
-    double* d_cam;  // (C,12) M = R*inv(K), t
-    double* cam_host;
-    int smem_per_sm;
-    Params prm;
-    int precision;
-    int tune_G, tune_ctas, tune_threads, no_fly, last_fly;
-    long long launches;
-    int last_grid, last_block, last_smem, last_G;
-    // device staging owned by the handle (snowtri_run_host only)
-    void* stage[6];
-    size_t stage_cap[6];
-    char err[512];
-};
-
 static char g_err[512] = "";
-
-static int fail(snowtri_t* h, int code, const char* fmt, ...) {
-    char* dst = h ? h->err : g_err;
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(dst, 512, fmt, ap);
-    va_end(ap);
-    return code;
-}
-
-#define CUDA_TRY(h, call)                                                                      \
-    do {                                                                                       \
-        cudaError_t e_ = (call);                                                               \
-        if (e_ != cudaSuccess)                                                                 \
-            return fail(h, SNOWTRI_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                        __FILE__, __LINE__);                                                   \
-    } while (0)
+char* snowtri_global_error() { return g_err; }
 
 static void inv3(const double* m, double* o) {
     const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7], i = m[8];
@@ -146,7 +115,7 @@ extern "C" int snowtri_set_params(snowtri_t* h, double kst, double ast, double d
 
 extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_precision: NULL handle");
-    if (precision != SNOWTRI_PREC_F64 && precision != SNOWTRI_PREC_F32)
+    if (precision != SNOWTRI_PREC_F64 && precision != SNOWTRI_PREC_F32 && precision != SNOWTRI_PREC_MIXED)
         return fail(h, SNOWTRI_E_ARG, "snowtri_set_precision: unknown precision %d", precision);
     h->precision = precision;
     return SNOWTRI_OK;
@@ -154,8 +123,10 @@ extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
 
 extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_tuning: NULL handle");
-    if (threads != 0 && threads != 256 && threads != 512 && threads != -256)
-        return fail(h, SNOWTRI_E_ARG, "snowtri_set_tuning: threads must be 0 (auto), 256, 512 or -256");
+    if (threads != 0 && threads != 256 && threads != 512 && threads != -256 && threads != -1)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_set_tuning: threads must be 0 (auto), 256, 512, -256 or -1");
+    h->no_p1 = threads != 0 ? 1 : 0;         /* any explicit block size selects the general fused kernel */
+    if (threads == -1) threads = 0;
     h->tune_G = frames_per_group > 0 ? frames_per_group : 0;
     h->tune_ctas = max_ctas > 0 ? max_ctas : 0;
     h->no_fly = threads == -256 ? 1 : 0;   /* -256: 256 threads with stored rays even when P == 1 */
@@ -164,6 +135,11 @@ extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ct
 }
 
 extern "C" long long snowtri_launch_count(snowtri_t* h) { return h ? h->launches : 0; }
+
+extern "C" const char* snowtri_last_kernel(snowtri_t* h) {
+    if (!h || h->launches == 0) return "";
+    return h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused");
+}
 
 extern "C" int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group) {
     if (!h) return SNOWTRI_E_ARG;
@@ -365,6 +341,8 @@ extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_sco
     if (((uintptr_t)d_kpts & 7u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_run: d_kpts must be 8-byte aligned");
     CUDA_TRY(h, cudaSetDevice(h->device));
 
+    if (snowtri_p1_eligible(h, P, Pout))
+        return snowtri_p1_run(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
     const int rc = h->precision == SNOWTRI_PREC_F32
                        ? run_fused<float>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream)
                        : run_fused<double>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);

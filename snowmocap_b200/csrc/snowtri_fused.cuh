@@ -2,18 +2,13 @@
 // batch of frames (reference main.py:55-71 per frame; camera.py:234-253, triangulation.py:24-162).
 // See DESIGN.md ("fused kernel") for the shared-memory layout and the phase structure.
 #pragma once
+#include "snowtri_internal.h"
 #include "snowtri_math.cuh"
 
 namespace snowtri {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kCliqueMax = 8;  // the register-resident fuse path handles up to 8 cameras
-
-struct Params {
-    double kst, ast, dthr, cond_tol, score_tol;
-    float kst_f;  // smallest float >= kst: (float s < kst_f) <=> ((double)s < kst)
-    int num_tol, center;
-};
 
 // Byte offsets of the shared-memory regions of the fused kernel (computed on the host).
 struct FusedSmem {

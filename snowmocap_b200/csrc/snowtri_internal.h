@@ -1,0 +1,57 @@
+// Internals shared by the translation units of libsnowtri.so (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "snowtri.h"
+#include "snowtri_math.cuh"
+
+namespace snowtri {
+struct Params {
+    double kst, ast, dthr, cond_tol, score_tol;
+    float kst_f;  // smallest float >= kst: (float s < kst_f) <=> ((double)s < kst)
+    int num_tol, center;
+};
+}  // namespace snowtri
+
+char* snowtri_global_error();  // message buffer used when there is no handle (create failures)
+
+struct snowtri_handle {
+    int device, C, sm_count, max_smem;
+    double* d_cam;  // (C,12) M = R*inv(K), t
+    double* cam_host;
+    int smem_per_sm;
+    snowtri::Params prm;
+    int precision;
+    int tune_G, tune_ctas, tune_threads, no_fly, last_fly, no_p1;
+    long long launches;
+    int last_grid, last_block, last_smem, last_G;
+    // device staging owned by the handle (snowtri_run_host only)
+    void* stage[6];
+    size_t stage_cap[6];
+    char err[512];
+};
+
+static inline int fail(snowtri_t* h, int code, const char* fmt, ...) {
+    char* dst = h ? h->err : snowtri_global_error();
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, SNOWTRI_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+
+// single-person path (snowtri_p1.cu)
+bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout);
+int snowtri_p1_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
+                   int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream);

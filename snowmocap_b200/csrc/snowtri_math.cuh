@@ -43,7 +43,11 @@ __device__ __forceinline__ double rsqrt_t(double x) {
 }
 
 // Fused-path variant: one Newton step (relative error ~2e-14 in double), MUFU.RSQ in float.
-__device__ __forceinline__ float rsqrt_fast(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;  // flush-to-zero form: no denormal rescaling around the MUFU (q.q is never denormal for real rays)
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ double rsqrt_fast(double x) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -102,6 +106,32 @@ __device__ __forceinline__ PairSol<T> pair_solve_a(const V3<T>& hm, T A, const V
     return s;
 }
 
+// Cross-product form used by the single-person kernel: with n = hm x hs, |n|^2 = det and
+// d.n = +-dist*|n|, so q.q = det*(d.n)^2 without forming q.  The normal-equation part (det, n0, n1)
+// is well conditioned; d.n is the difference of nearly equal terms when the rays nearly intersect,
+// which is why the mixed mode evaluates cross_dot in float64.
+template <typename T>
+struct PairSolN {
+    T det, n0, n1;
+};
+template <typename T>
+__device__ __forceinline__ PairSolN<T> pair_solve_n(const V3<T>& hm, T A, const V3<T>& hs, T Cc, const V3<T>& d) {
+    const T B = dot3(hm, hs), D = dot3(hm, d), E = dot3(hs, d);
+    PairSolN<T> s;
+    s.det = fma(A, Cc, -(B * B));
+    s.n0 = fma(Cc, D, -(B * E));
+    s.n1 = fma(A, E, -(B * D));
+    return s;
+}
+template <typename T>
+__device__ __forceinline__ T cross_dot(const V3<T>& hm, const V3<T>& hs, const V3<T>& d) {
+    V3<T> n;
+    n.x = fma(hm.y, hs.z, -(hm.z * hs.y));
+    n.y = fma(hm.z, hs.x, -(hm.x * hs.z));
+    n.z = fma(hm.x, hs.y, -(hm.y * hs.x));
+    return dot3(n, d);
+}
+
 // g = gated (sm+ss)*0.00025*rsqrt(q.q); the reference's score is 2*g*det.
 template <typename T>
 __device__ __forceinline__ T gated_g(const PairSol<T>& s, float sm, float ss, float kst_f, T dthr) {
@@ -119,6 +149,15 @@ __device__ __forceinline__ V3<T> pair_v(const PairSol<T>& s, const V3<T>& hm, co
     v.x = fma(hm.x, s.n0, -(hs.x * s.n1));
     v.y = fma(hm.y, s.n0, -(hs.y * s.n1));
     v.z = fma(hm.z, s.n0, -(hs.z * s.n1));
+    return v;
+}
+
+template <typename T>
+__device__ __forceinline__ V3<T> pair_v(T n0, T n1, const V3<T>& hm, const V3<T>& hs) {
+    V3<T> v;
+    v.x = fma(hm.x, n0, -(hs.x * n1));
+    v.y = fma(hm.y, n0, -(hs.y * n1));
+    v.z = fma(hm.z, n0, -(hs.z * n1));
     return v;
 }
 
@@ -157,6 +196,16 @@ __device__ __forceinline__ V3<T> back_project(const T* __restrict__ M, T u, T v)
     h.x = fma(M[0], u, fma(M[1], v, M[2]));
     h.y = fma(M[3], u, fma(M[4], v, M[5]));
     h.z = fma(M[6], u, fma(M[7], v, M[8]));
+    return h;
+}
+
+// Same with the rows of M padded to 4 entries (16-byte aligned rows in the constant bank).
+template <typename T>
+__device__ __forceinline__ V3<T> back_project4(const T* __restrict__ M, T u, T v) {
+    V3<T> h;
+    h.x = fma(M[0], u, fma(M[1], v, M[2]));
+    h.y = fma(M[4], u, fma(M[5], v, M[6]));
+    h.z = fma(M[8], u, fma(M[9], v, M[10]));
     return h;
 }
 

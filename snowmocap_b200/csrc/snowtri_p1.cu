@@ -1,0 +1,126 @@
+// Host side of the single-person kernel (snowtri_p1.cuh): constant tables, tile size, launch.
+#include <math.h>
+#include <string.h>
+
+#include "snowtri_internal.h"
+#include "snowtri_p1.cuh"
+
+using namespace snowtri;
+
+// ---- single-person path (snowtri_p1.cuh) -------------------------------------------------------
+template <typename T, typename TD, int C>
+static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
+                    int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream) {
+    constexpr int NP = C * (C - 1) / 2;
+    constexpr int NT = 256, NW = NT / 32;
+    static P1Args<T, C> a;  // > 1 KB: keep it off the stack; a handle is not thread-safe anyway
+    memset(&a, 0, sizeof(a));
+    a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
+    a.out = d_out; a.pscores = d_pscores; a.nout = d_nout;
+    a.F = F; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
+    a.center = h->prm.center; a.num_tol = h->prm.num_tol; a.kst_f = h->prm.kst_f;
+    const double inv = h->prm.dthr > 0.0 ? 1.0 / h->prm.dthr : (double)INFINITY;
+    a.inv_dthr = (T)inv;
+    a.inv_dthr64 = inv;
+    const double band = sizeof(TD) == 8 ? kGuardBandMixed : kGuardBandF32;
+    a.guard_lo = isinf(inv) ? (T)INFINITY : (T)(inv * (1.0 - band));
+    a.guard_hi = isinf(inv) ? (T)INFINITY : (T)(inv * (1.0 + band));
+    a.guard_w = (isinf(inv) || sizeof(T) == 8) ? 0.f : (float)(inv * band);
+    a.tol2 = h->prm.cond_tol >= 0.0 ? h->prm.cond_tol * h->prm.cond_tol : -1.0;
+    a.kscale[0] = (T)0;
+    for (int n = 1; n <= NP; ++n) a.kscale[n] = (T)(0.0005 / (double)n);
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < 9; ++k) {
+            a.cam64[12 * c + (k / 3) * 4 + k % 3] = h->cam_host[12 * c + k];
+            a.camc[12 * c + (k / 3) * 4 + k % 3] = (T)h->cam_host[12 * c + k];
+        }
+    for (int x = 0; x < C - 1; ++x)
+        for (int y = x + 1; y < C; ++y) {
+            const int e = pair_index(C, x, y);
+            a.px[e] = (unsigned char)x;
+            a.py[e] = (unsigned char)y;
+            for (int k = 0; k < 3; ++k) {
+                const double tm = h->cam_host[12 * x + 9 + k], ts = h->cam_host[12 * y + 9 + k];
+                a.pd64[e * 8 + k] = ts - tm;
+                a.pd64[e * 8 + 4 + k] = (tm + ts) / 2;
+                a.pdc[e * 8 + k] = (T)(ts - tm);
+                a.pdc[e * 8 + 4 + k] = (T)((tm + ts) / 2);
+            }
+        }
+    auto kern = p1_kernel<T, TD, C, NT>;
+    int occ = 0;
+    auto smem_of = [&](int gw) -> size_t { return (size_t)NW * ((size_t)gw * NP * 24 + (size_t)gw * 128 + (((size_t)gw * Pout * 4 + 7) & ~(size_t)7)); };
+    // frames per warp tile: few wasted lanes in the last 32-item step, enough tiles to fill every warp slot
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8) > 49152 ? (int)smem_of(8) : 49152) != cudaSuccess)
+        cudaGetLastError();
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_of(8));
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)h->sm_count * occ * NW;
+    int Gw = 1;
+    double best = -1.0;
+    for (int gw = 32; gw >= 1; gw >>= 1) {
+        if (gw > 8 && smem_of(gw) * occ > (size_t)h->smem_per_sm - 4096) continue;
+        const long long items = (long long)gw * keypoint_num;
+        const double eff = (double)items / (double)((items + 31) / 32 * 32);
+        const long long nt = ((long long)F + gw - 1) / gw;
+        const double fill = nt >= 4 * slots ? 1.0 : (double)nt / (double)(4 * slots);
+        const double centre = (double)(gw * NP) / (double)((gw * NP + 31) / 32 * 32);  // lanes busy in the centre step
+        const double score = eff * (0.25 + 0.75 * fill) * (0.9 + 0.1 * centre);
+        if (score > best + 1e-9) { best = score; Gw = gw; }
+    }
+    if (h->tune_G > 0) Gw = h->tune_G > 32 ? 32 : h->tune_G;
+    a.Gw = Gw;
+    const size_t smem = smem_of(Gw);
+    if (smem > (size_t)h->max_smem)
+        return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_run: single-person path needs %zu B of shared memory (Pout=%d)", smem, Pout);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
+    if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel attribute: %s", cudaGetErrorString(e));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (occ < 1) occ = 1;
+    const int ntiles = (F + Gw - 1) / Gw;
+    int grid = h->sm_count * occ;
+    if (grid > (ntiles + NW - 1) / NW) grid = (ntiles + NW - 1) / NW;
+    if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+    kern<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel launch failed: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    h->last_grid = grid; h->last_block = NT; h->last_smem = (int)smem; h->last_G = Gw;
+    h->last_fly = 2;
+    return SNOWTRI_OK;
+}
+
+template <typename T, typename TD>
+static int run_p1(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
+                  int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream) {
+#define P1_CASE(CC) \
+    case CC: return run_p1_c<T, TD, CC>(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream)
+    switch (h->C) {
+#ifdef P1_ONLY_C
+        P1_CASE(P1_ONLY_C);
+#else
+        P1_CASE(2); P1_CASE(3); P1_CASE(4); P1_CASE(5); P1_CASE(6); P1_CASE(7); P1_CASE(8);
+#endif
+    }
+#undef P1_CASE
+    return fail(h, SNOWTRI_E_UNSUPPORTED, "single-person path supports 2..8 cameras");
+}
+
+
+bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout) {
+    const bool all_kept = h->prm.ast <= 0.0 && h->prm.kst >= 0.0;
+    const bool never_filter = h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0;
+    return !h->no_p1 && P == 1 && h->C >= 2 && h->C <= 8 && all_kept && never_filter && Pout <= 64;
+}
+
+int snowtri_p1_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
+                   int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream) {
+    switch (h->precision) {
+        case SNOWTRI_PREC_F32:
+            return run_p1<float, float>(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+        case SNOWTRI_PREC_MIXED:
+            return run_p1<float, double>(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+        default:
+            return run_p1<double, double>(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+    }
+}

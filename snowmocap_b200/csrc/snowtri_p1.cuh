@@ -1,0 +1,397 @@
+// Single-person fused kernel (P == 1, C <= 8 cameras): the shipped configuration of the reference
+// (configs/snowmocap_default_config.json: one performer, average_score_threshold 0, condense_score_tol 0)
+// and BASELINE configs[0]/[1].  Same result as fused_kernel, different mapping onto the machine:
+//
+//   * warp-autonomous: every warp owns tiles of `Gw` consecutive frames and walks them alone; the
+//     only synchronisation is __syncwarp(), so no CTA barrier ever stalls the FP pipes;
+//   * lanes run over the flattened (frame, joint) index of the tile: 32 consecutive joints of one
+//     camera row are one coalesced 256-byte read, and a tile of Gw*J items wastes < 32 lanes;
+//     the (u,v,score) of the NEXT item are loaded into registers before the current one is solved,
+//     so HBM latency is hidden by the ~400 instructions of an item and not by occupancy;
+//   * with one person per camera a candidate IS a camera pair, so a cluster is a bit mask over the
+//     C(C-1)/2 pairs.  The greedy clustering (reference triangulation.py:107-134) runs per frame in
+//     one lane on bit masks; the fuse (reference :138-148) is a fully unrolled loop over the pairs
+//     with camera and pair constants in the kernel-parameter constant bank.  When every lane of the
+//     warp has the full clique (the normal case) the loop is branch-free;
+//   * the rays of a joint are built once in registers and shared by all pairs;
+//   * sum(score * point) is accumulated as  sum(w*mid) + 1/2 * sum_c alpha_c * h_c  with one scalar
+//     alpha per camera instead of a 3-vector per pair (see snowtri_math.cuh for the algebra);
+//   * the person score (mean keypoint score, reference :150) is accumulated in registers per lane,
+//     parked in a per-warp shared-memory column when the lane crosses a frame boundary and reduced
+//     with a fixed-order warp shuffle: deterministic, no re-read of the output.
+//
+// Precision (template T = bulk arithmetic, TD = arithmetic of the ray-distance numerator d.(hm x hs)):
+//   <double,double>  everything in float64, like the reference.
+//   <float,double>   "mixed": rays, normal equations and the fuse in float32; the ill-conditioned
+//                    distance numerator (two nearly intersecting rays) in float64.
+//   <float,float>    everything in float32.
+//   In both float modes every DISCRETE decision is float64: the clustering centres always, and the
+//   distance gate (dist > dthr) is re-evaluated in float64 whenever the float32 value lies within
+//   the guard band of the threshold (cold path p1_item_exact).
+// Requirements (checked by the host): P == 1, all_kept (ast <= 0, kst >= 0) and never_filter
+// (score_tol <= 0, kst >= 0); anything else takes fused_kernel.
+#pragma once
+#include <math.h>
+
+#include <type_traits>
+
+#include "snowtri_math.cuh"
+
+namespace snowtri {
+
+// relative half-width of the guard band around 1/dthr inside which the gate is re-decided in float64
+constexpr double kGuardBandF32 = 4e-3;
+constexpr double kGuardBandMixed = 2e-5;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// pair index of cameras x < y in the reference's (mc, sc) enumeration order
+__host__ __device__ constexpr int pair_index(int C, int x, int y) { return x * C - x * (x + 1) / 2 + y - x - 1; }
+
+// compile-time loop over the camera pairs x < y in the reference's order: f(integral_constant x, y)
+template <int C, int X = 0, int Y = 1, typename F>
+__device__ __forceinline__ void static_for_pairs(F&& f) {
+    if constexpr (X < C - 1) {
+        f(std::integral_constant<int, X>{}, std::integral_constant<int, Y>{});
+        if constexpr (Y + 1 < C) static_for_pairs<C, X, Y + 1>(f);
+        else static_for_pairs<C, X + 1, X + 2>(f);
+    }
+}
+
+template <typename T, int C>
+struct P1Args {
+    static constexpr int NP = C * (C - 1) / 2;
+    const float* kpts;    // (F,C,1,J,2)
+    const float* scores;  // (F,C,1,J)
+    const int* counts;    // (F,C) or null
+    float* out;           // (F,Pout,Jout,4)
+    float* pscores;       // (F,Pout)
+    int* nout;            // (F)
+    int F, J, Jout, Pout, Gw, center, num_tol;
+    float kst_f;
+    T inv_dthr;
+    float guard_w;         // float modes: re-decide in float64 when |1/dist - 1/dthr| < guard_w (0 = never)
+    T guard_lo, guard_hi;  // same band as an interval (cold path)
+    double inv_dthr64, tol2;
+    T kscale[NP + 1];                  // 0.0005 / n  (score unit and the division by the cluster size, Q6/Q10)
+    alignas(16) T camc[C * 12];        // M = R*inv(K), row-major, rows padded to 4
+    alignas(16) T pdc[NP * 8];         // per pair: d = ts - tm (3), pad, mid = (tm + ts)/2 (3), pad
+    alignas(16) double cam64[C * 12];  // float64 copies: clustering centres, guard band, mixed mode
+    alignas(16) double pd64[NP * 8];
+    unsigned char px[NP], py[NP];
+};
+
+// Cold path: one (frame, slot, joint) item pair by pair in a rolled loop, with the distance gate of
+// every pair inside the guard band decided in float64 from the raw pixel coordinates.  Also used
+// for the second and later clusters of a frame.  `kp`/`sp` point at the item's camera-0 entry.
+template <typename T, typename TD, int C>
+__device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2* __restrict__ kp,
+                                             const float* __restrict__ sp, unsigned mask) {
+    constexpr int NP = C * (C - 1) / 2;
+    T S = (T)0, X = (T)0, Y = (T)0, Z = (T)0;
+    for (int e = 0; e < NP; ++e) {
+        if (!((mask >> e) & 1u)) continue;
+        const int x = a.px[e], y = a.py[e];
+        const float2 pm = kp[(size_t)x * a.J], ps = kp[(size_t)y * a.J];
+        const float sm = sp[(size_t)x * a.J], ss = sp[(size_t)y * a.J];
+        if (sm < a.kst_f || ss < a.kst_f) continue;
+        const V3<T> hm = back_project4<T>(a.camc + 12 * x, (T)pm.x, (T)pm.y);
+        const V3<T> hs = back_project4<T>(a.camc + 12 * y, (T)ps.x, (T)ps.y);
+        const V3<double> hm64 = back_project4<double>(a.cam64 + 12 * x, (double)pm.x, (double)pm.y);
+        const V3<double> hs64 = back_project4<double>(a.cam64 + 12 * y, (double)ps.x, (double)ps.y);
+        V3<T> d;
+        d.x = a.pdc[e * 8]; d.y = a.pdc[e * 8 + 1]; d.z = a.pdc[e * 8 + 2];
+        V3<double> d64;
+        d64.x = a.pd64[e * 8]; d64.y = a.pd64[e * 8 + 1]; d64.z = a.pd64[e * 8 + 2];
+        const PairSolN<T> s = pair_solve_n(hm, dot3(hm, hm), hs, dot3(hs, hs), d);
+        T dn;
+        if constexpr (sizeof(TD) == 8) dn = (T)cross_dot(hm64, hs64, d64);
+        else dn = cross_dot(hm, hs, d);
+        const T r = rsqrt_fast(s.det * dn * dn);
+        const T rd = r * s.det;
+        bool far = rd < a.inv_dthr;
+        if (sizeof(T) == 4 && rd > a.guard_lo && rd < a.guard_hi) {
+            const PairSol<double> s64 = pair_solve(hm64, hs64, d64);
+            far = rsqrt_fast(s64.qq) * s64.det < a.inv_dthr64;
+        }
+        if (far) continue;
+        const T gq = ((T)sm + (T)ss) * r;
+        const T w = gq * s.det;
+        const V3<T> vv = pair_v(s.n0, s.n1, hm, hs);
+        S += w;
+        X = fma(w, a.pdc[e * 8 + 4], fma((T)0.5 * gq, vv.x, X));
+        Y = fma(w, a.pdc[e * 8 + 5], fma((T)0.5 * gq, vv.y, Y));
+        Z = fma(w, a.pdc[e * 8 + 6], fma((T)0.5 * gq, vv.z, Z));
+    }
+    if (S == (T)0) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const T rS = rcp_t(S);
+    return make_float4((float)(X * rS), (float)(Y * rS), (float)(Z * rS), (float)(S * a.kscale[__popc(mask)]));
+}
+
+// resident CTAs per SM the register allocation is held to (256-thread CTAs)
+template <typename T, typename TD, int C>
+constexpr int p1_min_blocks() {
+#ifdef P1_MINB
+    return P1_MINB;
+#else
+    return sizeof(T) == 4 ? (C <= 4 ? 2 : 1) : (C <= 3 ? 2 : 1);
+#endif
+}
+
+template <typename T, typename TD, int C, int NT>
+__global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(const __grid_constant__ P1Args<T, C> a) {
+    constexpr int NP = C * (C - 1) / 2;
+    constexpr int NW = NT / 32;
+    constexpr unsigned ALL = (NP >= 32) ? 0xffffffffu : ((1u << NP) - 1u);
+    constexpr bool MIXED = sizeof(TD) != sizeof(T);
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int J = a.J, Jout = a.Jout, Pout = a.Pout, Gw = a.Gw;
+    // per-warp scratch: centres (Gw*NP*3 doubles), person-score columns (Gw*32 floats), cluster masks (Gw*Pout words)
+    const int warp_bytes = Gw * NP * 24 + Gw * 128 + ((Gw * Pout * 4 + 7) & ~7);
+    double* cen = reinterpret_cast<double*>(smem + (size_t)warp * warp_bytes);
+    float* part = reinterpret_cast<float*>(cen + Gw * NP * 3);
+    uint32_t* meta = reinterpret_cast<uint32_t*>(part + Gw * 32);
+
+    const float2* kp2 = reinterpret_cast<const float2*>(a.kpts);
+    const int ntiles = (a.F + Gw - 1) / Gw;
+    const int CJ = C * J;
+
+    for (int tile = warp * gridDim.x + blockIdx.x; tile < ntiles; tile += NW * gridDim.x) {
+        const int f0 = tile * Gw;
+        const int Gc = min(Gw, a.F - f0);
+        const int nitems = Gc * Jout;
+        const float2* kpt = kp2 + (size_t)f0 * CJ;
+        const float* sct = a.scores + (size_t)f0 * CJ;
+        float4* outt = reinterpret_cast<float4*>(a.out) + (size_t)f0 * Pout * Jout;
+
+        // (frame, joint) of this lane's first item; lanes past the end redo the last item and store nothing
+        int g = 0, j = lane;
+        while (j >= Jout) {
+            j -= Jout;
+            ++g;
+        }
+        if (lane >= nitems) {
+            g = Gc - 1;
+            j = Jout - 1;
+        }
+        // ---- first item's inputs: in flight while the tile's clustering runs ---------------------------
+        float2 p2n[C];
+        float s1n[C];
+        {
+            const int off = g * CJ + j;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                p2n[c] = __ldg(kpt + off + c * J);
+                s1n[c] = __ldg(sct + off + c * J);
+            }
+        }
+
+        // ---- centre-joint midpoint of every candidate, float64 (reference triangulation.py:112,124) ----
+        for (int idx = lane; idx < Gc * NP; idx += 32) {
+            const int gg = idx / NP, e = idx - gg * NP;
+            const int x = a.px[e], y = a.py[e];
+            const size_t fb = (size_t)gg * CJ + a.center;
+            const float2 pm = __ldg(kpt + fb + (size_t)x * J), ps = __ldg(kpt + fb + (size_t)y * J);
+            const V3<double> hm = back_project4<double>(a.cam64 + 12 * x, (double)pm.x, (double)pm.y);
+            const V3<double> hs = back_project4<double>(a.cam64 + 12 * y, (double)ps.x, (double)ps.y);
+            V3<double> d, mid;
+            d.x = a.pd64[e * 8]; d.y = a.pd64[e * 8 + 1]; d.z = a.pd64[e * 8 + 2];
+            mid.x = a.pd64[e * 8 + 4]; mid.y = a.pd64[e * 8 + 5]; mid.z = a.pd64[e * 8 + 6];
+            const PairSol<double> s = pair_solve(hm, hs, d);
+            const V3<double> w = pair_midpoint(s, hm, hs, mid);
+            cen[3 * idx] = w.x;
+            cen[3 * idx + 1] = w.y;
+            cen[3 * idx + 2] = w.z;
+        }
+        for (int gg = 0; gg < Gc; ++gg) part[gg * 32 + lane] = 0.f;
+        __syncwarp();
+
+        // ---- greedy clustering on pair bit masks, one lane per frame (reference :107-134) ----------
+        int K = 0;
+        if (lane < Gc) {
+            unsigned present = (1u << C) - 1u;
+            if (a.counts) {
+                present = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) present |= (a.counts[(size_t)(f0 + lane) * C + c] > 0 ? 1u : 0u) << c;
+            }
+            unsigned valid = 0;  // the reference's candidate list, in list order (bit e = pair e)
+#pragma unroll
+            for (int x = 0; x < C - 1; ++x)
+#pragma unroll
+                for (int y = x + 1; y < C; ++y)
+                    if ((present >> x) & (present >> y) & 1u) valid |= 1u << pair_index(C, x, y);
+            if (valid) {
+                const int last = 31 - __clz(valid);
+                unsigned mains = valid & ~(1u << last);  // the last candidate is never a main (Q1/Q2)
+                unsigned absorbed = 0;
+                const double* cg = cen + 3 * lane * NP;
+                while (mains) {
+                    const int m = __ffs(mains) - 1;
+                    mains &= mains - 1;
+                    if ((absorbed >> m) & 1u) continue;
+                    const double mx = cg[3 * m], my = cg[3 * m + 1], mz = cg[3 * m + 2];
+                    unsigned mask = 1u << m;
+                    unsigned rest = valid & ~absorbed & ~((2u << m) - 1u);
+                    while (rest) {
+                        const int i = __ffs(rest) - 1;
+                        rest &= rest - 1;
+                        const double dx = mx - cg[3 * i], dy = my - cg[3 * i + 1], dz = mz - cg[3 * i + 2];
+                        if (!((dx * dx + dy * dy + dz * dz) > a.tol2)) {  // distance to the MAIN (Q3); NaN absorbs
+                            mask |= 1u << i;
+                            absorbed |= 1u << i;
+                        }
+                    }
+                    if (__popc(mask) >= a.num_tol) {  // otherwise its members stay absorbed (Q5)
+                        if (K < Pout) meta[lane * Pout + K] = mask;
+                        ++K;
+                    }
+                }
+            }
+            for (int k = K; k < Pout; ++k) meta[lane * Pout + k] = 0u;
+            a.nout[f0 + lane] = K;
+        }
+        const bool multi = __any_sync(kFullMask, K > 1) && Pout > 1;  // some frame has a second cluster
+        __syncwarp();
+
+        // ---- fuse: lanes over the flattened (frame, joint) index of the tile ---------------------------
+        float acc = 0.f;  // this lane's share of the person score of frame `gacc`
+        int gacc = g;
+        for (int q0 = 0; q0 < nitems; q0 += 32) {
+            const bool live = q0 + lane < nitems;
+            const int off = g * CJ + j;
+            V3<T> h[C];
+            V3<TD> hd[MIXED ? C : 1];
+            T A[C], sc[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                h[c] = back_project4<T>(a.camc + 12 * c, (T)p2n[c].x, (T)p2n[c].y);
+                if constexpr (MIXED) hd[c] = back_project4<TD>(a.cam64 + 12 * c, (TD)p2n[c].x, (TD)p2n[c].y);
+                A[c] = dot3(h[c], h[c]);
+                // a score below the keypoint threshold kills every pair of its camera: poison it so that
+                // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
+                sc[c] = s1n[c] < a.kst_f ? (T)-1e30 : (T)s1n[c];
+            }
+            // next item of this lane: issue its loads now, use them one iteration later
+            int gn = g, jn = j + 32;
+            while (jn >= Jout) {
+                jn -= Jout;
+                ++gn;
+            }
+            if (q0 + 32 + lane >= nitems) {
+                gn = Gc - 1;
+                jn = Jout - 1;
+            }
+            if (q0 + 32 < nitems) {
+                const int offn = gn * CJ + jn;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    p2n[c] = __ldg(kpt + offn + c * J);
+                    s1n[c] = __ldg(sct + offn + c * J);
+                }
+            }
+
+            // output slot 0: the unrolled path
+            const unsigned mask = meta[g * Pout];
+            const bool full = __all_sync(kFullMask, mask == ALL);
+            T S = (T)0, Xm = (T)0, Ym = (T)0, Zm = (T)0;
+            T al[C];
+            float margin = INFINITY;  // float modes: smallest |1/dist - 1/dthr| over the pairs
+#pragma unroll
+            for (int c = 0; c < C; ++c) al[c] = (T)0;
+            auto pair = [&](auto xc, auto yc) {
+                constexpr int x = decltype(xc)::value, y = decltype(yc)::value;
+                constexpr int e = pair_index(C, x, y);
+                V3<T> d;
+                d.x = a.pdc[e * 8]; d.y = a.pdc[e * 8 + 1]; d.z = a.pdc[e * 8 + 2];
+                const PairSolN<T> s = pair_solve_n(h[x], A[x], h[y], A[y], d);
+                T dn;
+                if constexpr (MIXED) {
+                    V3<TD> dd;
+                    dd.x = a.pd64[e * 8]; dd.y = a.pd64[e * 8 + 1]; dd.z = a.pd64[e * 8 + 2];
+                    dn = (T)cross_dot(hd[x], hd[y], dd);
+                } else {
+                    dn = cross_dot(h[x], h[y], d);
+                }
+                const T r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
+                const T rd = r * s.det;                   // 1/dist
+                if constexpr (sizeof(T) == 4) margin = fminf(margin, fabsf(rd - a.inv_dthr));
+                T gq = fmax(sc[x] + sc[y], (T)0) * r;
+                if (rd < a.inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
+                const T w = gq * s.det;
+                S += w;
+                al[x] = fma(gq, s.n0, al[x]);
+                al[y] = fma(-gq, s.n1, al[y]);
+                Xm = fma(w, a.pdc[e * 8 + 4], Xm);
+                Ym = fma(w, a.pdc[e * 8 + 5], Ym);
+                Zm = fma(w, a.pdc[e * 8 + 6], Zm);
+            };
+            if (full) {
+                static_for_pairs<C>([&](auto xc, auto yc) { pair(xc, yc); });
+            } else {
+                static_for_pairs<C>([&](auto xc, auto yc) {
+                    if ((mask >> pair_index(C, decltype(xc)::value, decltype(yc)::value)) & 1u) pair(xc, yc);
+                });
+            }
+            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (sizeof(T) == 4 && margin < a.guard_w && mask) {
+                // a float32 distance within the guard band of dthr: decide in float64
+                o = p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mask);
+            } else if (S != (T)0) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
+                T X = (T)0, Y = (T)0, Z = (T)0;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    X = fma(al[c], h[c].x, X);
+                    Y = fma(al[c], h[c].y, Y);
+                    Z = fma(al[c], h[c].z, Z);
+                }
+                const T rS = rcp_t(S);
+                o.x = (float)(fma((T)0.5, X, Xm) * rS);
+                o.y = (float)(fma((T)0.5, Y, Ym) * rS);
+                o.z = (float)(fma((T)0.5, Z, Zm) * rS);
+                o.w = (float)(S * a.kscale[__popc(mask)]);
+            }
+            if (live) {
+                outt[(g * Pout) * Jout + j] = o;
+                if (g != gacc) {
+                    part[gacc * 32 + lane] = acc;
+                    acc = 0.f;
+                    gacc = g;
+                }
+                acc += o.w;
+                // further clusters of the same frame are rare with one person per camera: rolled cold path
+                for (int k = 1; k < Pout; ++k) {
+                    const unsigned mk = multi ? meta[g * Pout + k] : 0u;
+                    outt[(g * Pout + k) * Jout + j] =
+                        mk ? p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            g = gn;
+            j = jn;
+        }
+        if (lane < nitems) part[gacc * 32 + lane] = acc;
+        __syncwarp();
+
+        // ---- person score = mean keypoint score (reference :150) ----------------------------------------
+        for (int gg = 0; gg < Gc; ++gg) {
+            const float s = warp_sum(part[gg * 32 + lane]);
+            if (lane == 0) a.pscores[(size_t)(f0 + gg) * Pout] = s / (float)Jout;
+        }
+        if (!multi) {
+            for (int row = lane; row < Gc * Pout; row += 32)
+                if (row % Pout) a.pscores[(size_t)f0 * Pout + row] = 0.f;
+        } else {  // rows of later clusters, just written by this warp: read back (rare)
+            for (int row = 0; row < Gc * Pout; ++row) {
+                if (row % Pout == 0) continue;
+                const float4* o = reinterpret_cast<const float4*>(a.out) + ((size_t)f0 * Pout + row) * Jout;
+                float s = 0.f;
+                for (int jj = lane; jj < Jout; jj += 32) s += __ldcg(&o[jj].w);
+                s = warp_sum(s);
+                if (lane == 0) a.pscores[(size_t)f0 * Pout + row] = s / (float)Jout;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace snowtri

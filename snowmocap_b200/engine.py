@@ -69,7 +69,7 @@ class TriangulationEngine:
                                                 int(p["center"])), self._h)
 
     def set_precision(self, precision):
-        code = {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32}[precision]
+        code = {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32, "mixed": _lib.PREC_MIXED}[precision]
         _lib.check(self._lib.snowtri_set_precision(self._h, code), self._h)
         self.precision = precision
 
@@ -83,7 +83,8 @@ class TriangulationEngine:
     def last_launch_info(self):
         g, b, s, fg = ct.c_int(), ct.c_int(), ct.c_int(), ct.c_int()
         self._lib.snowtri_last_launch_info(self._h, ct.byref(g), ct.byref(b), ct.byref(s), ct.byref(fg))
-        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "frames_per_group": fg.value}
+        return {"grid": g.value, "block": b.value, "smem_bytes": s.value, "frames_per_group": fg.value,
+                "kernel": (self._lib.snowtri_last_kernel(self._h) or b"").decode()}
 
     def close(self):
         if self._h:
