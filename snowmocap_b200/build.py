@@ -41,6 +41,7 @@ def _flags(verbose):
         fl = ["-ccbin", "/usr/bin/g++"] + fl
     if verbose:
         fl.append("-Xptxas=-v")
+    fl += os.environ.get("SNOWTRI_NVCC_FLAGS", "").split()   # experiments only (e.g. -DP1_MINB=3)
     return fl
 
 

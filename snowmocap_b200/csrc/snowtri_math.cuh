@@ -71,6 +71,15 @@ __device__ __forceinline__ double rcp_t(double x) {
     return r;
 }
 
+// 1/x for positive finite normal x without the range checks of __frcp_rn: MUFU.RCP + one Newton step
+// (float, <= 1 ulp); the double version is rcp_t.
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+__device__ __forceinline__ double rcp_fast(double x) { return rcp_t(x); }
+
 template <typename T>
 struct PairSol {
     T det, n0, n1, qq;
@@ -206,6 +215,23 @@ __device__ __forceinline__ V3<T> back_project4(const T* __restrict__ M, T u, T v
     h.x = fma(M[0], u, fma(M[1], v, M[2]));
     h.y = fma(M[4], u, fma(M[5], v, M[6]));
     h.z = fma(M[8], u, fma(M[9], v, M[10]));
+    return h;
+}
+
+// Hide how a value was derived so that the compiler keeps it in a register instead of
+// re-deriving it inside a hot loop (per-tile base pointers, constant addends).
+__device__ __forceinline__ void keep_in_register(float& x) { asm volatile("" : "+f"(x)); }
+__device__ __forceinline__ void keep_in_register(double& x) { asm volatile("" : "+d"(x)); }
+template <typename P>
+__device__ __forceinline__ void keep_in_register(P*& p) { asm volatile("" : "+l"(p)); }
+
+// h = M[:,0]*u + M[:,1]*v + addend, the addend M[:,2] passed in registers (rows of M padded to 4)
+template <typename T>
+__device__ __forceinline__ V3<T> back_project4r(const T* __restrict__ M, const T* addend, T u, T v) {
+    V3<T> h;
+    h.x = fma(M[0], u, fma(M[1], v, addend[0]));
+    h.y = fma(M[4], u, fma(M[5], v, addend[1]));
+    h.z = fma(M[8], u, fma(M[9], v, addend[2]));
     return h;
 }
 

@@ -12,7 +12,11 @@ template <typename T, typename TD, int C>
 static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
                     int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream) {
     constexpr int NP = C * (C - 1) / 2;
+#ifdef P1_NT
+    constexpr int NT = P1_NT, NW = NT / 32;
+#else
     constexpr int NT = 256, NW = NT / 32;
+#endif
     static P1Args<T, C> a;  // > 1 KB: keep it off the stack; a handle is not thread-safe anyway
     memset(&a, 0, sizeof(a));
     a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
@@ -55,17 +59,19 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
         cudaGetLastError();
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_of(8));
     if (occ < 1) occ = 1;
+    // frames per warp tile: few wasted lanes in the last 32-item step and in the centre step, not longer
+    // than the contiguous frame range a warp owns
     const long long slots = (long long)h->sm_count * occ * NW;
+    const long long range = ((long long)F + slots - 1) / slots;
     int Gw = 1;
     double best = -1.0;
     for (int gw = 32; gw >= 1; gw >>= 1) {
         if (gw > 8 && smem_of(gw) * occ > (size_t)h->smem_per_sm - 4096) continue;
+        if (gw > 1 && gw > range) continue;
         const long long items = (long long)gw * keypoint_num;
         const double eff = (double)items / (double)((items + 31) / 32 * 32);
-        const long long nt = ((long long)F + gw - 1) / gw;
-        const double fill = nt >= 4 * slots ? 1.0 : (double)nt / (double)(4 * slots);
         const double centre = (double)(gw * NP) / (double)((gw * NP + 31) / 32 * 32);  // lanes busy in the centre step
-        const double score = eff * (0.25 + 0.75 * fill) * (0.9 + 0.1 * centre);
+        const double score = eff * (0.9 + 0.1 * centre);
         if (score > best + 1e-9) { best = score; Gw = gw; }
     }
     if (h->tune_G > 0) Gw = h->tune_G > 32 ? 32 : h->tune_G;
@@ -77,9 +83,8 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel attribute: %s", cudaGetErrorString(e));
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
     if (occ < 1) occ = 1;
-    const int ntiles = (F + Gw - 1) / Gw;
-    int grid = h->sm_count * occ;
-    if (grid > (ntiles + NW - 1) / NW) grid = (ntiles + NW - 1) / NW;
+    int grid = h->sm_count * occ;               // one frame range per warp; a short batch uses fewer CTAs
+    if ((long long)grid * NW > F) grid = (F + NW - 1) / NW;
     if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();

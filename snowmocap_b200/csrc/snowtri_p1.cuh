@@ -127,6 +127,9 @@ __device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2
     return make_float4((float)(X * rS), (float)(Y * rS), (float)(Z * rS), (float)(S * a.kscale[__popc(mask)]));
 }
 
+#ifndef P1_KEEP
+#define P1_KEEP 1
+#endif
 // resident CTAs per SM the register allocation is held to (256-thread CTAs)
 template <typename T, typename TD, int C>
 constexpr int p1_min_blocks() {
@@ -153,15 +156,39 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
     uint32_t* meta = reinterpret_cast<uint32_t*>(part + Gw * 32);
 
     const float2* kp2 = reinterpret_cast<const float2*>(a.kpts);
-    const int ntiles = (a.F + Gw - 1) / Gw;
     const int CJ = C * J;
+    // Each warp owns one contiguous range of frames and walks it tile by tile: its input is two
+    // sequential streams (kpts, scores).  (An explicit L2 look-ahead with cp.async.bulk.prefetch.L2 was
+    // measured and made the kernel 8-10 % slower; the register prefetch of the next item is enough.)
+    const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
+    const int fa = (int)((long long)a.F * gwarp / nwarps), fb = (int)((long long)a.F * (gwarp + 1) / nwarps);
+    T m2[C][3];  // constant addends of the rays (third column of M): an FFMA takes one constant-bank operand only
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            m2[c][k] = a.camc[12 * c + 4 * k + 2];
+#if P1_KEEP
+            keep_in_register(m2[c][k]);
+#endif
+        }
 
-    for (int tile = warp * gridDim.x + blockIdx.x; tile < ntiles; tile += NW * gridDim.x) {
-        const int f0 = tile * Gw;
-        const int Gc = min(Gw, a.F - f0);
+    for (int f0 = fa; f0 < fb; f0 += Gw) {
+        const int Gc = min(Gw, fb - f0);
         const int nitems = Gc * Jout;
         const float2* kpt = kp2 + (size_t)f0 * CJ;
         const float* sct = a.scores + (size_t)f0 * CJ;
+        const float2* kpc[C];  // per-camera rows of the tile: one 64-bit add per load in the item loop
+        const float* scc[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            kpc[c] = kpt + c * J;
+            scc[c] = sct + c * J;
+#if P1_KEEP
+            keep_in_register(kpc[c]);
+            keep_in_register(scc[c]);
+#endif
+        }
         float4* outt = reinterpret_cast<float4*>(a.out) + (size_t)f0 * Pout * Jout;
 
         // (frame, joint) of this lane's first item; lanes past the end redo the last item and store nothing
@@ -181,8 +208,8 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
             const int off = g * CJ + j;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                p2n[c] = __ldg(kpt + off + c * J);
-                s1n[c] = __ldg(sct + off + c * J);
+                p2n[c] = __ldg(kpc[c] + off);
+                s1n[c] = __ldg(scc[c] + off);
             }
         }
 
@@ -265,7 +292,7 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
             T A[C], sc[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                h[c] = back_project4<T>(a.camc + 12 * c, (T)p2n[c].x, (T)p2n[c].y);
+                h[c] = back_project4r<T>(a.camc + 12 * c, m2[c], (T)p2n[c].x, (T)p2n[c].y);
                 if constexpr (MIXED) hd[c] = back_project4<TD>(a.cam64 + 12 * c, (TD)p2n[c].x, (TD)p2n[c].y);
                 A[c] = dot3(h[c], h[c]);
                 // a score below the keypoint threshold kills every pair of its camera: poison it so that
@@ -274,9 +301,16 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
             }
             // next item of this lane: issue its loads now, use them one iteration later
             int gn = g, jn = j + 32;
-            while (jn >= Jout) {
-                jn -= Jout;
-                ++gn;
+            if (Jout >= 32) {  // at most one frame boundary per step
+                if (jn >= Jout) {
+                    jn -= Jout;
+                    ++gn;
+                }
+            } else {
+                while (jn >= Jout) {
+                    jn -= Jout;
+                    ++gn;
+                }
             }
             if (q0 + 32 + lane >= nitems) {
                 gn = Gc - 1;
@@ -286,8 +320,8 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
                 const int offn = gn * CJ + jn;
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    p2n[c] = __ldg(kpt + offn + c * J);
-                    s1n[c] = __ldg(sct + offn + c * J);
+                    p2n[c] = __ldg(kpc[c] + offn);
+                    s1n[c] = __ldg(scc[c] + offn);
                 }
             }
 
@@ -345,11 +379,11 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
                     Y = fma(al[c], h[c].y, Y);
                     Z = fma(al[c], h[c].z, Z);
                 }
-                const T rS = rcp_t(S);
+                const T rS = rcp_fast(S);
                 o.x = (float)(fma((T)0.5, X, Xm) * rS);
                 o.y = (float)(fma((T)0.5, Y, Ym) * rS);
                 o.z = (float)(fma((T)0.5, Z, Zm) * rS);
-                o.w = (float)(S * a.kscale[__popc(mask)]);
+                o.w = (float)(S * (full ? a.kscale[NP] : a.kscale[__popc(mask)]));
             }
             if (live) {
                 outt[(g * Pout) * Jout + j] = o;
