@@ -40,11 +40,16 @@ enum {
 };
 
 /* Compute precision of the fused path (snowtri_run*).  The candidate/condense entry points
- * always compute in float64 like the reference. */
+ * always compute in float64 like the reference.  The float modes apply to the single-person kernel
+ * (one person per camera, shipped thresholds); every other case computes in float64 unless
+ * SNOWTRI_PREC_F32_EXPERIMENTAL is selected. */
 enum {
     SNOWTRI_PREC_F64 = 0,      /* float64 arithmetic throughout (default; matches the reference) */
     SNOWTRI_PREC_F32 = 1,      /* float32 arithmetic, float64 re-evaluation of decisions near a threshold */
-    SNOWTRI_PREC_MIXED = 2     /* float32 arithmetic, float64 for the ray-distance numerator and the decisions */
+    SNOWTRI_PREC_MIXED = 2,    /* float32 arithmetic, float64 for the ray-distance numerator and the decisions */
+    SNOWTRI_PREC_F32_EXPERIMENTAL = 3 /* like F32, and also float32 in the general kernel with several persons per
+                                  camera: decisions (nout, membership) stay exact, but joints of wrongly
+                                  matched "ghost" clusters are only good to ~1e-3; F32/MIXED use float64 there */
 };
 
 /* Camera parameter container on the device; replaces Camera/CameraGroup's K, R, t
@@ -79,11 +84,16 @@ int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const 
                 int F, int P, int J, int keypoint_num, int Pout,
                 float* d_out, float* d_pscores, int* d_nout, void* stream);
 
-/* Same through HOST buffers (pinned memory recommended): H2D copies, snowtri_run, D2H copies,
- * then waits for completion.  This is the call a reference-side plugin makes. */
+/* Same through HOST buffers (pinned memory recommended).  The batch is cut into chunks that flow
+ * through two internal streams (ordered after `stream`): chunk i's results travel device->host while
+ * chunk i+1's inputs travel host->device and are triangulated, so both PCIe directions stay busy.
+ * Returns after everything has arrived.  This is the call a reference-side plugin makes. */
 int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, const int* h_counts,
                      int F, int P, int J, int keypoint_num, int Pout,
                      float* h_out, float* h_pscores, int* h_nout, void* stream);
+
+/* Frames per chunk of snowtri_run_host's copy/compute pipeline (0 = automatic, about 24 MB of input). */
+int snowtri_set_pipeline(snowtri_t* h, int frames_per_chunk);
 
 /* Human_Triangulation alone (reference snowvision/triangulation.py:50-93), float64 results.
  * Candidates are written at their DENSE index n = ((pair*P + pm)*P + ps), pair enumerating

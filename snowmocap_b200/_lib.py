@@ -8,7 +8,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libsnowtri.so")
 
 OK, E_ARG, E_CUDA, E_UNSUPPORTED, E_NOMEM = 0, -1, -2, -3, -4
-PREC_F64, PREC_F32, PREC_MIXED = 0, 1, 2
+PREC_F64, PREC_F32, PREC_MIXED, PREC_F32_EXPERIMENTAL = 0, 1, 2, 3
 
 # Every symbol include/snowtri.h declares: name -> (restype, argtypes)
 _P, _I, _D = ct.c_void_p, ct.c_int, ct.c_double
@@ -18,6 +18,7 @@ SYMBOLS = {
     "snowtri_set_params": (_I, [_P, _D, _D, _D, _D, _I, _D, _I]),
     "snowtri_set_precision": (_I, [_P, _I]),
     "snowtri_set_tuning": (_I, [_P, _I, _I, _I]),
+    "snowtri_set_pipeline": (_I, [_P, _I]),
     "snowtri_run": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "snowtri_run_host": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "snowtri_candidates": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),

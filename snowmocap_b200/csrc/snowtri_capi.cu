@@ -95,6 +95,12 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 6; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->pipe_in) {
+        cudaStreamDestroy(h->pipe_in);
+        cudaStreamDestroy(h->pipe_out);
+        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i) cudaEventDestroy(h->pipe_ev[i]);
+        cudaEventDestroy(h->pipe_start);
+    }
     if (h->d_cam) cudaFree(h->d_cam);
     free(h->cam_host);
     free(h);
@@ -115,9 +121,11 @@ extern "C" int snowtri_set_params(snowtri_t* h, double kst, double ast, double d
 
 extern "C" int snowtri_set_precision(snowtri_t* h, int precision) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_precision: NULL handle");
-    if (precision != SNOWTRI_PREC_F64 && precision != SNOWTRI_PREC_F32 && precision != SNOWTRI_PREC_MIXED)
+    if (precision != SNOWTRI_PREC_F64 && precision != SNOWTRI_PREC_F32 && precision != SNOWTRI_PREC_MIXED &&
+        precision != SNOWTRI_PREC_F32_EXPERIMENTAL)
         return fail(h, SNOWTRI_E_ARG, "snowtri_set_precision: unknown precision %d", precision);
-    h->precision = precision;
+    h->allow_f32_multi = precision == SNOWTRI_PREC_F32_EXPERIMENTAL ? 1 : 0;
+    h->precision = precision == SNOWTRI_PREC_F32_EXPERIMENTAL ? SNOWTRI_PREC_F32 : precision;
     return SNOWTRI_OK;
 }
 
@@ -131,6 +139,12 @@ extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ct
     h->tune_ctas = max_ctas > 0 ? max_ctas : 0;
     h->no_fly = threads == -256 ? 1 : 0;   /* -256: 256 threads with stored rays even when P == 1 */
     h->tune_threads = threads == -256 ? 256 : threads;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_set_pipeline(snowtri_t* h, int frames_per_chunk) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_pipeline: NULL handle");
+    h->tune_chunk = frames_per_chunk > 0 ? frames_per_chunk : 0;
     return SNOWTRI_OK;
 }
 
@@ -343,7 +357,14 @@ extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_sco
 
     if (snowtri_p1_eligible(h, P, Pout))
         return snowtri_p1_run(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
-    const int rc = h->precision == SNOWTRI_PREC_F32
+    // The general kernel computes in float32 only on request AND for one person per camera: with several
+    // persons, wrongly matched ("ghost") clusters fuse midpoints that lie metres apart, so the float32
+    // error of the 1/distance weights (1e-4..1e-3) moves their joints beyond the 1e-4 parity bound.
+    // (Its float32 keep decision is guarded by a float64 re-evaluation, see fused_kernel phase 1a.)
+    // A positive condense_score_tol or kst < 0 also computes in float64: that filter has no guard.
+    const bool never_filter = h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0;
+    const bool f32_ok = h->precision == SNOWTRI_PREC_F32 && never_filter && (P == 1 || h->allow_f32_multi);
+    const int rc = f32_ok
                        ? run_fused<float>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream)
                        : run_fused<double>(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
     return rc;
@@ -375,17 +396,48 @@ extern "C" int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* 
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    CUDA_TRY(h, cudaMemcpyAsync(h->stage[0], h_kpts, need[0], cudaMemcpyHostToDevice, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h->stage[1], h_scores, need[1], cudaMemcpyHostToDevice, st));
-    if (h_counts) CUDA_TRY(h, cudaMemcpyAsync(h->stage[2], h_counts, need[2], cudaMemcpyHostToDevice, st));
-    int rc = snowtri_run(h, (const float*)h->stage[0], (const float*)h->stage[1],
-                         h_counts ? (const int*)h->stage[2] : nullptr, F, P, J, keypoint_num, Pout,
-                         (float*)h->stage[3], (float*)h->stage[4], (int*)h->stage[5], stream);
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h_out, h->stage[3], need[3], cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h_pscores, h->stage[4], need[4], cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaMemcpyAsync(h_nout, h->stage[5], need[5], cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
+    // Chunked pipeline over two internal streams: chunk i's device->host copy (stream `out`) overlaps
+    // chunk i+1's host->device copy and kernel (stream `in`), so the PCIe link carries both directions
+    // at once.  Small batches go through in one chunk.
+    if (!h->pipe_in) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pipe_in, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pipe_out, cudaStreamNonBlocking));
+        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i)
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_start, cudaEventDisableTiming));
+    }
+    const size_t in_per_frame = (size_t)h->C * P * J * 12;
+    int chunk = h->tune_chunk > 0 ? h->tune_chunk : (int)((size_t)(24u << 20) / in_per_frame);  // ~24 MB of input per chunk
+    if (chunk < 1) chunk = 1;
+    if (chunk > F) chunk = F;
+    const int nchunks = (F + chunk - 1) / chunk;
+    CUDA_TRY(h, cudaEventRecord(h->pipe_start, st));            // order the pipeline after the caller's stream
+    CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_in, h->pipe_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_out, h->pipe_start, 0));
+    const size_t rpf = (size_t)h->C * P * J, opf = (size_t)Pout * keypoint_num;
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int f0 = ci * chunk, fc = F - f0 < chunk ? F - f0 : chunk;
+        float* dk = (float*)h->stage[0] + (size_t)f0 * rpf * 2;
+        float* ds = (float*)h->stage[1] + (size_t)f0 * rpf;
+        int* dc = (int*)h->stage[2] + (size_t)f0 * h->C;
+        float* dout = (float*)h->stage[3] + (size_t)f0 * opf * 4;
+        float* dps = (float*)h->stage[4] + (size_t)f0 * Pout;
+        int* dn = (int*)h->stage[5] + f0;
+        CUDA_TRY(h, cudaMemcpyAsync(dk, h_kpts + (size_t)f0 * rpf * 2, (size_t)fc * rpf * 8, cudaMemcpyHostToDevice, h->pipe_in));
+        CUDA_TRY(h, cudaMemcpyAsync(ds, h_scores + (size_t)f0 * rpf, (size_t)fc * rpf * 4, cudaMemcpyHostToDevice, h->pipe_in));
+        if (h_counts)
+            CUDA_TRY(h, cudaMemcpyAsync(dc, h_counts + (size_t)f0 * h->C, (size_t)fc * h->C * 4, cudaMemcpyHostToDevice, h->pipe_in));
+        const int rc = snowtri_run(h, dk, ds, h_counts ? dc : nullptr, fc, P, J, keypoint_num, Pout, dout, dps, dn, h->pipe_in);
+        if (rc) return rc;
+        cudaEvent_t ev = h->pipe_ev[ci % SNOWTRI_PIPE_EVENTS];
+        CUDA_TRY(h, cudaEventRecord(ev, h->pipe_in));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_out, ev, 0));
+        CUDA_TRY(h, cudaMemcpyAsync(h_out + (size_t)f0 * opf * 4, dout, (size_t)fc * opf * 16, cudaMemcpyDeviceToHost, h->pipe_out));
+        CUDA_TRY(h, cudaMemcpyAsync(h_pscores + (size_t)f0 * Pout, dps, (size_t)fc * Pout * 4, cudaMemcpyDeviceToHost, h->pipe_out));
+        CUDA_TRY(h, cudaMemcpyAsync(h_nout + f0, dn, (size_t)fc * 4, cudaMemcpyDeviceToHost, h->pipe_out));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->pipe_out));
+    CUDA_TRY(h, cudaStreamSynchronize(h->pipe_in));
     return SNOWTRI_OK;
 }
 

@@ -219,6 +219,47 @@ __device__ __forceinline__ T pair_weights(const PairSol<T>& s, T sa, bool low, T
     return g;
 }
 
+// Keep-phase variant for float32: the score w = c/dist has absolute error ~ w * (delta/dist) where
+// delta ~ 1e-5 m bounds the float32 error of the ray distance itself, so `err` accumulates w/dist and
+// the caller compares |sum - threshold| against delta*err.  A distance inside the guard band of dthr
+// (the gate could flip) poisons the bound with +inf.
+__device__ __forceinline__ float pair_weight_err(const PairSol<float>& s, float sa, bool low, float inv_dthr,
+                                                 float guard_w, float& err) {
+    const float r = rsqrt_fast(s.qq);
+    const float rd = r * s.det;  // = 1/dist
+    float w = sa * 0.0005f * rd;
+    if (!low && fabsf(rd - inv_dthr) < guard_w) err = INFINITY;
+    if (low || rd < inv_dthr) w = 0.f;
+    err = fmaf(w, rd, err);
+    return w;
+}
+constexpr float kDistDelta = 1e-5f;   // metres; bound on the float32 error of a ray-to-ray distance
+constexpr float kGateGuard = 4e-3f;   // relative half-width of the guard band around 1/dthr
+
+// Mean candidate score in float64 from the raw inputs in global memory, one warp, lanes over joints
+// (reference triangulation.py:70-79).  Cold path of the float32 kernel's keep decision.
+template <typename T>
+__device__ __noinline__ double candidate_mean_f64(const FusedArgs<T>& a, int f, int mc, int pm, int sc, int ps, int lane) {
+    const float2* kg = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * a.R;
+    const float* sg = a.scores + (size_t)f * a.R;
+    const int rm = (mc * a.P + pm) * a.J, rs = (sc * a.P + ps) * a.J;
+    V3<double> d;
+    d.x = a.cam[12 * sc + 9] - a.cam[12 * mc + 9];
+    d.y = a.cam[12 * sc + 10] - a.cam[12 * mc + 10];
+    d.z = a.cam[12 * sc + 11] - a.cam[12 * mc + 11];
+    double sum = 0.0;
+    for (int j = lane; j < a.J; j += 32) {
+        const float2 qm = kg[rm + j], qs = kg[rs + j];
+        const V3<double> hm = back_project<double>(a.cam + 12 * mc, (double)qm.x, (double)qm.y);
+        const V3<double> hs = back_project<double>(a.cam + 12 * sc, (double)qs.x, (double)qs.y);
+        const PairSol<double> s = pair_solve(hm, hs, d);
+        const double gg = gated_g(s, sg[rm + j], sg[rs + j], a.prm.kst_f, a.prm.dthr);
+        sum += (gg + gg) * s.det;
+    }
+    sum = warp_sum(sum);
+    return sum / (double)a.J;
+}
+
 // ------------------------------------------------------------------------------------------
 // Template: T compute type, NT threads, CM cameras of the unrolled clique path (0 = off),
 //           NCH joint chunks held in registers by phase 1a (0 = generic loop, any J),
@@ -293,6 +334,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
 
     const T inv_dthr = a.inv_dthr;
     const float kst_f = a.prm.kst_f;
+    const float gate_guard = isinf((float)a.inv_dthr) ? 0.f : (float)a.inv_dthr * kGateGuard;
     const float2* uv = nullptr;  // current group's (u,v) and scores (smem staging or global)
     const float* sv = nullptr;
 
@@ -428,6 +470,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
                     }
                     const int rs = ray_index(g, sc, ps, 0);
                     T sum = (T)0;
+                    float err = 0.f;  // float32 only: error bound of `sum` in units of kDistDelta
                     if constexpr (NCH > 0) {
 #pragma unroll
                         for (int ch = 0; ch < NCH; ++ch) {
@@ -438,7 +481,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
                                 get_ray(rs + j, sc, hs, ss);
                                 const PairSol<T> s = pair_solve_a(hm[ch], Am[ch], hs, dot3(hs, hs), d);
                                 T w;
-                                pair_weights(s, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, inv_dthr, w);
+                                if constexpr (sizeof(T) == 4)
+                                    w = pair_weight_err(s, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, inv_dthr, gate_guard, err);
+                                else
+                                    pair_weights(s, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, inv_dthr, w);
                                 sum += w;
                             }
                         }
@@ -450,33 +496,53 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
                             get_ray(rs + j, sc, hs, ss);
                             const PairSol<T> s = pair_solve(h0, hs, d);
                             T w;
-                            pair_weights(s, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, inv_dthr, w);
+                            if constexpr (sizeof(T) == 4)
+                                w = pair_weight_err(s, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, inv_dthr, gate_guard, err);
+                            else
+                                pair_weights(s, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, inv_dthr, w);
                             sum += w;
                         }
                     }
                     sum = warp_sum(sum);
-                    const double avg = (double)sum / (double)J;
+                    double avg = (double)sum / (double)J;
+                    if constexpr (sizeof(T) == 4) {
+                        // float32 sum closer to the threshold than its own error bound: the whole warp
+                        // redoes this candidate in float64 from the raw inputs (discrete decision)
+                        err = warp_sum(err);
+                        const double slack = (double)kDistDelta * (double)err + 1e-5 * fabs((double)sum);
+                        if (!(fabs((double)sum - a.prm.ast * (double)J) > slack))
+                            avg = candidate_mean_f64(a, f0 + g, mc, pm, sc, ps, lane);
+                    }
                     if (lane == 0) keep[nbase + ps] = (avg < a.prm.ast) ? 0 : 1;  // NaN mean is kept (Q9)
                 }
             }
             __syncthreads();
         }
         // ---- phase 1b: centre-joint midpoint of every kept candidate ------------------------
+        // Always float64 from the raw pixel coordinates (global memory, L2-resident after the staging
+        // copy): the clustering test |centre - main| > tol is a discrete decision and must not depend on
+        // the compute precision of the fuse.
         for (int n = tid; n < Gc * ncand; n += NT) {
             if (!keep[n]) continue;
             const int g = n / ncand, c = n - g * ncand;
             const int pair = c / PP, pm = (c / P) % P, ps = c % P;
             const int mc = pairs[pair].x, sc = pairs[pair].y;
-            V3<T> hm, hs, d, mid;
-            float s0, s1;
-            get_ray(ray_index(g, mc, pm, a.prm.center), mc, hm, s0);
-            get_ray(ray_index(g, sc, ps, a.prm.center), sc, hs, s1);
-            load_pd(pair, d, mid);
-            const PairSol<T> s = pair_solve(hm, hs, d);
-            const V3<T> w = pair_midpoint(s, hm, hs, mid);
-            cen[3 * n] = (double)w.x;
-            cen[3 * n + 1] = (double)w.y;
-            cen[3 * n + 2] = (double)w.z;
+            const float2* kg = reinterpret_cast<const float2*>(a.kpts) + (size_t)(f0 + g) * R;
+            const float2 qm = kg[(mc * P + pm) * J + a.prm.center], qs = kg[(sc * P + ps) * J + a.prm.center];
+            const V3<double> hm = back_project<double>(a.cam + 12 * mc, (double)qm.x, (double)qm.y);
+            const V3<double> hs = back_project<double>(a.cam + 12 * sc, (double)qs.x, (double)qs.y);
+            V3<double> d, mid;
+            d.x = a.cam[12 * sc + 9] - a.cam[12 * mc + 9];
+            d.y = a.cam[12 * sc + 10] - a.cam[12 * mc + 10];
+            d.z = a.cam[12 * sc + 11] - a.cam[12 * mc + 11];
+            mid.x = (a.cam[12 * mc + 9] + a.cam[12 * sc + 9]) / 2;
+            mid.y = (a.cam[12 * mc + 10] + a.cam[12 * sc + 10]) / 2;
+            mid.z = (a.cam[12 * mc + 11] + a.cam[12 * sc + 11]) / 2;
+            const PairSol<double> s = pair_solve(hm, hs, d);
+            const V3<double> w = pair_midpoint(s, hm, hs, mid);
+            cen[3 * n] = w.x;
+            cen[3 * n + 1] = w.y;
+            cen[3 * n + 2] = w.z;
         }
         __syncthreads();
 

@@ -17,6 +17,8 @@ struct Params {
 
 char* snowtri_global_error();  // message buffer used when there is no handle (create failures)
 
+#define SNOWTRI_PIPE_EVENTS 4
+
 struct snowtri_handle {
     int device, C, sm_count, max_smem;
     double* d_cam;  // (C,12) M = R*inv(K), t
@@ -29,6 +31,11 @@ struct snowtri_handle {
     int last_grid, last_block, last_smem, last_G;
     // device staging owned by the handle (snowtri_run_host only)
     void* stage[6];
+    // two-stream pipeline of snowtri_run_host
+    cudaStream_t pipe_in, pipe_out;
+    cudaEvent_t pipe_ev[SNOWTRI_PIPE_EVENTS], pipe_start;
+    int tune_chunk;  // frames per pipeline chunk (0 = automatic)
+    int allow_f32_multi;  // tests only: float32 general kernel with several persons per camera
     size_t stage_cap[6];
     char err[512];
 };

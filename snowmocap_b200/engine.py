@@ -69,12 +69,17 @@ class TriangulationEngine:
                                                 int(p["center"])), self._h)
 
     def set_precision(self, precision):
-        code = {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32, "mixed": _lib.PREC_MIXED}[precision]
+        code = {"f64": _lib.PREC_F64, "f32": _lib.PREC_F32, "mixed": _lib.PREC_MIXED,
+                "f32x": _lib.PREC_F32_EXPERIMENTAL}[precision]
         _lib.check(self._lib.snowtri_set_precision(self._h, code), self._h)
         self.precision = precision
 
     def set_tuning(self, frames_per_group=0, max_ctas=0, threads=0):
         _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas), int(threads)), self._h)
+
+    def set_pipeline(self, frames_per_chunk=0):
+        """Frames per chunk of run_host's copy/compute pipeline (0 = automatic)."""
+        _lib.check(self._lib.snowtri_set_pipeline(self._h, int(frames_per_chunk)), self._h)
 
     @property
     def launch_count(self):

@@ -270,15 +270,39 @@ def test_fused_without_counts_and_host_path(torch_cuda):
     assert eng.launch_count == 1
 
 
+@pytest.mark.parametrize("chunk", [0, 1, 37, 100000])
+def test_host_pipeline_chunks_match_device_path(torch_cuda, chunk):
+    """snowtri_run_host cuts the batch into chunks over two streams: same bytes as one device-side run."""
+    torch = torch_cuda
+    rig = floor_rig()
+    d = synth.make_frames(rig, 301, 1, 133, seed=11, low_score_frac=0.05, drop_prob=0.1)
+    eng = _engine(rig, synth.DEFAULT_PARAMS, precision="f32")
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    ref = eng.run(kp, sc, cn, Pout=2)
+    torch.cuda.synchronize()
+    eng.set_pipeline(chunk)
+    n0 = eng.launch_count
+    res = eng.run_host(d["kpts"], d["scores"], d["counts"], Pout=2)
+    assert eng.launch_count - n0 == (1 if chunk in (0, 100000) else -(-301 // chunk))
+    for k in ("out", "nout"):
+        assert np.array_equal(res[k], ref[k].cpu().numpy()), k
+    # the person score is a float32 sum whose lane partition depends on the frame's position in its tile
+    np.testing.assert_allclose(res["pscores"], ref["pscores"].cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("case", [0, 1, 2, 3])
-def test_fused_f32_mode_within_north_star(torch_cuda, case):
+@pytest.mark.parametrize("precision", ["f32", "mixed", "f32x"])
+def test_fused_float_modes_within_north_star(torch_cuda, case, precision):
+    """Float modes of snowtri_run on the general cases: persons emitted must be identical (every discrete
+    decision is float64-guarded) and the joints within the north_star bound.  "f32x" also runs the general
+    kernel in float32 with several persons, where ghost clusters are only good to ~1e-3."""
     torch = torch_cuda
     from oracle import c_oracle
     rname, F, P, J, prm, pout, kw = CASES[case]
     rig = _rig(rname)
     d = synth.make_frames(rig, F, P, J, seed=200 + case, **kw)
     ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
-    eng = _engine(rig, prm, precision="f32")
+    eng = _engine(rig, prm, precision=precision)
     kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
     res = eng.run(kp, sc, cn, Pout=pout)
     torch.cuda.synchronize()
@@ -286,7 +310,8 @@ def test_fused_f32_mode_within_north_star(torch_cuda, case):
     assert np.array_equal(nout, ref["nout"])
     m = np.minimum(ref["nout"], pout)
     valid = np.arange(pout)[None, :] < m[:, None]
-    assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < TOL_NORTH_STAR
+    tol = 2e-3 if (precision == "f32x" and P > 1) else TOL_NORTH_STAR
+    assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol
 
 
 def test_fused_equals_candidates_then_condense(torch_cuda):
