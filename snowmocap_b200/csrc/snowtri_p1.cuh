@@ -130,6 +130,14 @@ __device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2
 #ifndef P1_KEEP
 #define P1_KEEP 1
 #endif
+#ifndef P1_NI
+#define P1_NI 1   // items a lane solves side by side per step (1 or 2)
+#endif
+// Camera and pair constants come from the kernel-parameter constant bank.  (Baking them into the
+// instruction stream as immediates -- a kernel specialised per rig with NVRTC -- was measured with a
+// statically generated header: 0.535 -> 0.573 of the HBM roof at cfg2; not built this round.)
+#define P1_CAMC(T, i) (a.camc[i])
+#define P1_PDC(T, i) (a.pdc[i])
 // resident CTAs per SM the register allocation is held to (256-thread CTAs)
 template <typename T, typename TD, int C>
 constexpr int p1_min_blocks() {
@@ -146,6 +154,7 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
     constexpr int NW = NT / 32;
     constexpr unsigned ALL = (NP >= 32) ? 0xffffffffu : ((1u << NP) - 1u);
     constexpr bool MIXED = sizeof(TD) != sizeof(T);
+    constexpr int NI = P1_NI;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int J = a.J, Jout = a.Jout, Pout = a.Pout, Gw = a.Gw;
@@ -167,7 +176,7 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
     for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            m2[c][k] = a.camc[12 * c + 4 * k + 2];
+            m2[c][k] = P1_CAMC(T, 12 * c + 4 * k + 2);
 #if P1_KEEP
             keep_in_register(m2[c][k]);
 #endif
@@ -191,25 +200,48 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
         }
         float4* outt = reinterpret_cast<float4*>(a.out) + (size_t)f0 * Pout * Jout;
 
-        // (frame, joint) of this lane's first item; lanes past the end redo the last item and store nothing
-        int g = 0, j = lane;
-        while (j >= Jout) {
-            j -= Jout;
-            ++g;
+        // (frame, joint) of this lane's first NI items (item u of a step is 32*u further); lanes past the
+        // end redo the last item and store nothing
+        auto advance = [&](int& gg, int& jj) {  // 32 items further
+            jj += 32;
+            if (Jout >= 32) {  // at most one frame boundary
+                if (jj >= Jout) {
+                    jj -= Jout;
+                    ++gg;
+                }
+            } else {
+                while (jj >= Jout) {
+                    jj -= Jout;
+                    ++gg;
+                }
+            }
+        };
+        int g[NI], j[NI];
+        g[0] = 0;
+        j[0] = lane - 32;
+        advance(g[0], j[0]);
+#pragma unroll
+        for (int u = 1; u < NI; ++u) {
+            g[u] = g[u - 1];
+            j[u] = j[u - 1];
+            advance(g[u], j[u]);
         }
-        if (lane >= nitems) {
-            g = Gc - 1;
-            j = Jout - 1;
-        }
-        // ---- first item's inputs: in flight while the tile's clustering runs ---------------------------
-        float2 p2n[C];
-        float s1n[C];
-        {
-            const int off = g * CJ + j;
+#pragma unroll
+        for (int u = 0; u < NI; ++u)
+            if (32 * u + lane >= nitems) {
+                g[u] = Gc - 1;
+                j[u] = Jout - 1;
+            }
+        // ---- first items' inputs: in flight while the tile's clustering runs ---------------------------
+        float2 p2n[NI][C];
+        float s1n[NI][C];
+#pragma unroll
+        for (int u = 0; u < NI; ++u) {
+            const int off = g[u] * CJ + j[u];
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                p2n[c] = __ldg(kpc[c] + off);
-                s1n[c] = __ldg(scc[c] + off);
+                p2n[u][c] = __ldg(kpc[c] + off);
+                s1n[u][c] = __ldg(scc[c] + off);
             }
         }
 
@@ -282,126 +314,157 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
         __syncwarp();
 
         // ---- fuse: lanes over the flattened (frame, joint) index of the tile ---------------------------
+        // A step covers 32*NI consecutive items; a lane solves NI of them side by side (independent
+        // dependency chains, constants fetched once per pair).
         float acc = 0.f;  // this lane's share of the person score of frame `gacc`
-        int gacc = g;
-        for (int q0 = 0; q0 < nitems; q0 += 32) {
-            const bool live = q0 + lane < nitems;
-            const int off = g * CJ + j;
-            V3<T> h[C];
-            V3<TD> hd[MIXED ? C : 1];
-            T A[C], sc[C];
+        int gacc = g[0];
+        for (int q0 = 0; q0 < nitems; q0 += 32 * NI) {
+            V3<T> h[NI][C];
+            V3<TD> hd[NI][MIXED ? C : 1];
+            T A[NI][C], sc[NI][C];
+            int off[NI];
+            bool live[NI];
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
-                h[c] = back_project4r<T>(a.camc + 12 * c, m2[c], (T)p2n[c].x, (T)p2n[c].y);
-                if constexpr (MIXED) hd[c] = back_project4<TD>(a.cam64 + 12 * c, (TD)p2n[c].x, (TD)p2n[c].y);
-                A[c] = dot3(h[c], h[c]);
-                // a score below the keypoint threshold kills every pair of its camera: poison it so that
-                // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
-                sc[c] = s1n[c] < a.kst_f ? (T)-1e30 : (T)s1n[c];
-            }
-            // next item of this lane: issue its loads now, use them one iteration later
-            int gn = g, jn = j + 32;
-            if (Jout >= 32) {  // at most one frame boundary per step
-                if (jn >= Jout) {
-                    jn -= Jout;
-                    ++gn;
-                }
-            } else {
-                while (jn >= Jout) {
-                    jn -= Jout;
-                    ++gn;
-                }
-            }
-            if (q0 + 32 + lane >= nitems) {
-                gn = Gc - 1;
-                jn = Jout - 1;
-            }
-            if (q0 + 32 < nitems) {
-                const int offn = gn * CJ + jn;
+            for (int u = 0; u < NI; ++u) {
+                live[u] = q0 + 32 * u + lane < nitems;
+                off[u] = g[u] * CJ + j[u];
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    p2n[c] = __ldg(kpc[c] + offn);
-                    s1n[c] = __ldg(scc[c] + offn);
+                    h[u][c].x = fma(P1_CAMC(T, 12 * c + 0), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 1), (T)p2n[u][c].y, m2[c][0]));
+                    h[u][c].y = fma(P1_CAMC(T, 12 * c + 4), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 5), (T)p2n[u][c].y, m2[c][1]));
+                    h[u][c].z = fma(P1_CAMC(T, 12 * c + 8), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 9), (T)p2n[u][c].y, m2[c][2]));
+                    if constexpr (MIXED)
+                        hd[u][c] = back_project4<TD>(a.cam64 + 12 * c, (TD)p2n[u][c].x, (TD)p2n[u][c].y);
+                    A[u][c] = dot3(h[u][c], h[u][c]);
+                    // a score below the keypoint threshold kills every pair of its camera: poison it so that
+                    // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
+                    sc[u][c] = s1n[u][c] < a.kst_f ? (T)-1e30 : (T)s1n[u][c];
+                }
+            }
+            // next items of this lane: issue their loads now, use them one step later
+            int gn[NI], jn[NI];
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                gn[u] = g[u];
+                jn[u] = j[u];
+#pragma unroll
+                for (int k = 0; k < NI; ++k) advance(gn[u], jn[u]);
+                if (q0 + 32 * (NI + u) + lane >= nitems) {
+                    gn[u] = Gc - 1;
+                    jn[u] = Jout - 1;
+                }
+            }
+            if (q0 + 32 * NI < nitems) {
+#pragma unroll
+                for (int u = 0; u < NI; ++u) {
+                    const int offn = gn[u] * CJ + jn[u];
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        p2n[u][c] = __ldg(kpc[c] + offn);
+                        s1n[u][c] = __ldg(scc[c] + offn);
+                    }
                 }
             }
 
             // output slot 0: the unrolled path
-            const unsigned mask = meta[g * Pout];
-            const bool full = __all_sync(kFullMask, mask == ALL);
-            T S = (T)0, Xm = (T)0, Ym = (T)0, Zm = (T)0;
-            T al[C];
-            float margin = INFINITY;  // float modes: smallest |1/dist - 1/dthr| over the pairs
+            unsigned mask[NI];
+            bool allfull = true;
 #pragma unroll
-            for (int c = 0; c < C; ++c) al[c] = (T)0;
-            auto pair = [&](auto xc, auto yc) {
-                constexpr int x = decltype(xc)::value, y = decltype(yc)::value;
+            for (int u = 0; u < NI; ++u) {
+                mask[u] = meta[g[u] * Pout];
+                allfull = allfull && mask[u] == ALL;
+            }
+            const bool full = __all_sync(kFullMask, allfull);
+            T S[NI], Xm[NI], Ym[NI], Zm[NI], al[NI][C];
+            float margin[NI];  // float modes: smallest |1/dist - 1/dthr| over the pairs
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                S[u] = Xm[u] = Ym[u] = Zm[u] = (T)0;
+                margin[u] = INFINITY;
+#pragma unroll
+                for (int c = 0; c < C; ++c) al[u][c] = (T)0;
+            }
+            auto pair = [&](auto xc, auto yc, auto uc) {
+                constexpr int x = decltype(xc)::value, y = decltype(yc)::value, u = decltype(uc)::value;
                 constexpr int e = pair_index(C, x, y);
                 V3<T> d;
-                d.x = a.pdc[e * 8]; d.y = a.pdc[e * 8 + 1]; d.z = a.pdc[e * 8 + 2];
-                const PairSolN<T> s = pair_solve_n(h[x], A[x], h[y], A[y], d);
+                d.x = P1_PDC(T, e * 8); d.y = P1_PDC(T, e * 8 + 1); d.z = P1_PDC(T, e * 8 + 2);
+                const PairSolN<T> s = pair_solve_n(h[u][x], A[u][x], h[u][y], A[u][y], d);
                 T dn;
                 if constexpr (MIXED) {
                     V3<TD> dd;
                     dd.x = a.pd64[e * 8]; dd.y = a.pd64[e * 8 + 1]; dd.z = a.pd64[e * 8 + 2];
-                    dn = (T)cross_dot(hd[x], hd[y], dd);
+                    dn = (T)cross_dot(hd[u][x], hd[u][y], dd);
                 } else {
-                    dn = cross_dot(h[x], h[y], d);
+                    dn = cross_dot(h[u][x], h[u][y], d);
                 }
                 const T r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
                 const T rd = r * s.det;                   // 1/dist
-                if constexpr (sizeof(T) == 4) margin = fminf(margin, fabsf(rd - a.inv_dthr));
-                T gq = fmax(sc[x] + sc[y], (T)0) * r;
+                if constexpr (sizeof(T) == 4) margin[u] = fminf(margin[u], fabsf(rd - a.inv_dthr));
+                T gq = fmax(sc[u][x] + sc[u][y], (T)0) * r;
                 if (rd < a.inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
                 const T w = gq * s.det;
-                S += w;
-                al[x] = fma(gq, s.n0, al[x]);
-                al[y] = fma(-gq, s.n1, al[y]);
-                Xm = fma(w, a.pdc[e * 8 + 4], Xm);
-                Ym = fma(w, a.pdc[e * 8 + 5], Ym);
-                Zm = fma(w, a.pdc[e * 8 + 6], Zm);
+                S[u] += w;
+                al[u][x] = fma(gq, s.n0, al[u][x]);
+                al[u][y] = fma(-gq, s.n1, al[u][y]);
+                Xm[u] = fma(w, P1_PDC(T, e * 8 + 4), Xm[u]);
+                Ym[u] = fma(w, P1_PDC(T, e * 8 + 5), Ym[u]);
+                Zm[u] = fma(w, P1_PDC(T, e * 8 + 6), Zm[u]);
             };
             if (full) {
-                static_for_pairs<C>([&](auto xc, auto yc) { pair(xc, yc); });
+                static_for_pairs<C>([&](auto xc, auto yc) {
+                    pair(xc, yc, std::integral_constant<int, 0>{});
+                    if constexpr (NI > 1) pair(xc, yc, std::integral_constant<int, NI - 1>{});
+                });
             } else {
                 static_for_pairs<C>([&](auto xc, auto yc) {
-                    if ((mask >> pair_index(C, decltype(xc)::value, decltype(yc)::value)) & 1u) pair(xc, yc);
+                    constexpr int e = pair_index(C, decltype(xc)::value, decltype(yc)::value);
+                    if ((mask[0] >> e) & 1u) pair(xc, yc, std::integral_constant<int, 0>{});
+                    if constexpr (NI > 1)
+                        if ((mask[NI - 1] >> e) & 1u) pair(xc, yc, std::integral_constant<int, NI - 1>{});
                 });
             }
-            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (sizeof(T) == 4 && margin < a.guard_w && mask) {
-                // a float32 distance within the guard band of dthr: decide in float64
-                o = p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mask);
-            } else if (S != (T)0) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
-                T X = (T)0, Y = (T)0, Z = (T)0;
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    X = fma(al[c], h[c].x, X);
-                    Y = fma(al[c], h[c].y, Y);
-                    Z = fma(al[c], h[c].z, Z);
+            for (int u = 0; u < NI; ++u) {
+                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sizeof(T) == 4 && margin[u] < a.guard_w && mask[u]) {
+                    // a float32 distance within the guard band of dthr: decide in float64
+                    o = p1_item_exact<T, TD, C>(a, kpt + off[u], sct + off[u], mask[u]);
+                } else if (S[u] != (T)0) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
+                    T X = (T)0, Y = (T)0, Z = (T)0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        X = fma(al[u][c], h[u][c].x, X);
+                        Y = fma(al[u][c], h[u][c].y, Y);
+                        Z = fma(al[u][c], h[u][c].z, Z);
+                    }
+                    const T rS = rcp_fast(S[u]);
+                    o.x = (float)(fma((T)0.5, X, Xm[u]) * rS);
+                    o.y = (float)(fma((T)0.5, Y, Ym[u]) * rS);
+                    o.z = (float)(fma((T)0.5, Z, Zm[u]) * rS);
+                    o.w = (float)(S[u] * (full ? a.kscale[NP] : a.kscale[__popc(mask[u])]));
                 }
-                const T rS = rcp_fast(S);
-                o.x = (float)(fma((T)0.5, X, Xm) * rS);
-                o.y = (float)(fma((T)0.5, Y, Ym) * rS);
-                o.z = (float)(fma((T)0.5, Z, Zm) * rS);
-                o.w = (float)(S * (full ? a.kscale[NP] : a.kscale[__popc(mask)]));
+                if (live[u]) {
+                    outt[(g[u] * Pout) * Jout + j[u]] = o;
+                    if (g[u] != gacc) {
+                        part[gacc * 32 + lane] = acc;
+                        acc = 0.f;
+                        gacc = g[u];
+                    }
+                    acc += o.w;
+                    // further clusters of the same frame are rare with one person per camera: rolled cold path
+                    for (int k = 1; k < Pout; ++k) {
+                        const unsigned mk = multi ? meta[g[u] * Pout + k] : 0u;
+                        outt[(g[u] * Pout + k) * Jout + j[u]] =
+                            mk ? p1_item_exact<T, TD, C>(a, kpt + off[u], sct + off[u], mk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
             }
-            if (live) {
-                outt[(g * Pout) * Jout + j] = o;
-                if (g != gacc) {
-                    part[gacc * 32 + lane] = acc;
-                    acc = 0.f;
-                    gacc = g;
-                }
-                acc += o.w;
-                // further clusters of the same frame are rare with one person per camera: rolled cold path
-                for (int k = 1; k < Pout; ++k) {
-                    const unsigned mk = multi ? meta[g * Pout + k] : 0u;
-                    outt[(g * Pout + k) * Jout + j] =
-                        mk ? p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mk) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                g[u] = gn[u];
+                j[u] = jn[u];
             }
-            g = gn;
-            j = jn;
         }
         if (lane < nitems) part[gacc * 32 + lane] = acc;
         __syncwarp();
