@@ -164,11 +164,24 @@ def run_reference_arm(args, wl):
             "config": {"workload": wl, "description": desc, "C": C, "P": P, "J": J},
             "cpu_baseline": {"value": value, "unit": "keypoints/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
+def _emit(line):
+    """Print the one JSON line on the real stdout (fd saved before libraries could write banners to it)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    # NCCL / torchrun print banners on stdout; the driver wants exactly one JSON line there
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -378,7 +391,7 @@ def main():
             cv, threads, cdt = cpu_c_port(rig, P, J, prm, pout, min(cf, 200000))
             line["cpu_c_port"] = {"value": cv, "unit": "keypoints/s", "cores": threads, "kind": "port",
                                   "sample": f"{min(cf, 200000)} frames in {cdt:.2f} s, C/OpenMP restatement (oracle/snow_oracle.c)"}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

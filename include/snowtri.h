@@ -118,6 +118,26 @@ int snowtri_condense(snowtri_t* h, const double* d_cand, const int* d_ncand, int
 int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs,
                      const double* d_tm, const double* d_ts, double* d_dist, double* d_mid, void* stream);
 
+/* Human_Triangulation_Smooth (reference snowvision/triangulation.py:4-22, 164-186; called frame after frame
+ * by main.py:72-78): one second-order follower per (person, joint), float64 state kept on the device so a
+ * clip can be streamed in batches of consecutive frames.  f, z, r are the reference's smooth_f/z/r.
+ *   d_out      (F, Pout, J, 4) float32 (snowtri_run layout) or float64 (snowtri_condense layout): x, y, z are
+ *              replaced in place by the smoothed point, the score passes through
+ *   d_nout     (F) persons in each frame (as written by snowtri_run / snowtri_condense)
+ *   d_nsmooth  (F) persons in the smoothed list: the first frame of a clip passes through unchanged and
+ *              fixes n0 = its person count; later frames give min(nout, n0) -- the reference zips persons
+ *              with the followers created on the first frame, so later persons are dropped and followers of
+ *              absent persons are not advanced.  Slots >= d_nsmooth[f] are left untouched.
+ * The frame loop is sequential inside one launch (the recurrence is); max_persons bounds n0. */
+typedef struct snowtri_smooth_state snowtri_smooth_t;
+int snowtri_smooth_create(snowtri_t* h, snowtri_smooth_t** out, int max_persons, int J, double f, double z, double r);
+int snowtri_smooth_destroy(snowtri_smooth_t* s);
+int snowtri_smooth_reset(snowtri_t* h, snowtri_smooth_t* s, void* stream);   /* next frame starts a new clip */
+int snowtri_smooth_run(snowtri_t* h, snowtri_smooth_t* s, float* d_out, const int* d_nout, int* d_nsmooth,
+                       int F, int Pout, int J, double delta_time, void* stream);
+int snowtri_smooth_run_f64(snowtri_t* h, snowtri_smooth_t* s, double* d_out, const int* d_nout, int* d_nsmooth,
+                           int F, int Pout, int J, double delta_time, void* stream);
+
 /* Introspection. */
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */

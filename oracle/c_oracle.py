@@ -30,8 +30,11 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, "libsnow_oracle.so")
-        if not os.path.exists(path):
-            build()
+        try:
+            build()            # make: rebuilds only when snow_oracle.c is newer than the library
+        except Exception:
+            if not os.path.exists(path):
+                raise
         L = ct.CDLL(path)
         L.snow_oracle_fused.restype = ct.c_int
         L.snow_oracle_fused.argtypes = [ct.c_int] * 4 + [_f32, _f32, ct.c_void_p, _f64, _f64, _f64,
@@ -47,6 +50,9 @@ def lib():
                                            ct.c_int, ct.c_int, ct.c_int, _f64, _f64, _f64]
         L.snow_oracle_skew_ray.restype = None
         L.snow_oracle_skew_ray.argtypes = [ct.c_int, _f64, _f64, _f64, _f64, _f64, _f64]
+        L.snow_oracle_smooth.restype = ct.c_int
+        L.snow_oracle_smooth.argtypes = [ct.c_int, ct.c_int, ct.c_int, _f64, _i32, _i32, ct.c_double, ct.c_double,
+                                         ct.c_double, ct.c_double, _f64]
         L.snow_oracle_max_threads.restype = ct.c_int
         _LIB = L
     return _LIB
@@ -136,3 +142,16 @@ def skew_ray(hm, hs, tm, ts):
     W = np.zeros((n, 3))
     lib().snow_oracle_skew_ray(n, hm, hs, tm, ts, dist, W)
     return dist, W
+
+
+def smooth(points, nout, f=2.0, z=0.75, r=0.0, delta_time=1 / 30, state=None):
+    """Human_Triangulation_Smooth over consecutive frames, dense layout: points (F,P,J,3) f64, nout (F,).
+    Returns (smoothed points, nsm (F,), state) -- pass `state` back in to continue the same clip."""
+    pts = np.array(points, np.float64, order="C", copy=True)
+    F, P, J, _ = pts.shape
+    nout = np.ascontiguousarray(nout, np.int32)
+    nsm = np.zeros(F, np.int32)
+    if state is None:
+        state = np.zeros(2 + 3 * P * J * 3, np.float64)
+    lib().snow_oracle_smooth(F, P, J, pts, nout, nsm, float(f), float(z), float(r), float(delta_time), state)
+    return pts, nsm, state

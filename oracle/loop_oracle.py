@@ -154,3 +154,44 @@ def fused_frame(kpts, scores, counts, K, R, t, params):
     return condense_frame(tri, tol=params["cond_tol"], num_tol=params["num_tol"],
                           score_tol=params["score_tol"], center=params["center"],
                           keypoint_num=params.get("keypoint_num", J))
+
+
+# ---------------------------------------------------------------------------------------------
+# Temporal smoothing (the step after the hot path)
+class SecondOrderDynamic:
+    """Restatement of reference snowvision/triangulation.py:4-22 (semi-implicit Euler follower)."""
+
+    def __init__(self, f, z, r, x0):
+        pi = np.pi
+        self.k1 = z / (pi * f)                            # :7
+        self.k2 = 1 / ((2 * pi * f) * (2 * pi * f))       # :8
+        self.k3 = r * z / (2 * pi * f)                    # :9
+        self.xp = x0                                      # :11
+        self.y = x0                                       # :12
+        self.yd = 0                                       # :13
+
+    def update(self, T, x):
+        xd = (x - self.xp) / T                            # :17
+        self.xp = x                                       # :18
+        self.y = self.y + T * self.yd                     # :20
+        self.yd = self.yd + T * (x + self.k3 * xd - self.y - self.k1 * self.yd) / self.k2   # :21
+        return self.y
+
+
+def smooth_sequence(points_per_frame, f=2, z=0.75, r=0, delta_time=1 / 30):
+    """Human_Triangulation_Smooth (reference snowvision/triangulation.py:164-186) applied frame after frame
+    the way main.py:72-78 does.  points_per_frame: list of (n_t, J, 3) float64 arrays.  Returns the list of
+    smoothed (m_t, J, 3) arrays: the first frame passes through and creates one follower per (person, joint);
+    later frames zip persons with the followers of the FIRST frame by list position (persons beyond that are
+    dropped, followers of absent persons are not advanced)."""
+    sods, out = None, []
+    for pts in points_per_frame:
+        pts = [np.asarray(p, np.float64) for p in pts]
+        if sods is None:                                  # :177-184 first frame
+            sods = [[SecondOrderDynamic(f, z, r, p) for p in person] for person in pts]
+            out.append(np.array(pts, np.float64).reshape(len(pts), -1, 3) if pts else np.zeros((0, 0, 3)))
+        else:                                             # :168-176
+            damped = [[sod.update(delta_time, p) for p, sod in zip(person, psods)]
+                      for person, psods in zip(pts, sods)]
+            out.append(np.array(damped, np.float64).reshape(len(damped), -1, 3) if damped else np.zeros((0, 0, 3)))
+    return out

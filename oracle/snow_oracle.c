@@ -292,3 +292,38 @@ int snow_oracle_max_threads(void) {
     return 1;
 #endif
 }
+
+
+/* Human_Triangulation_Smooth over consecutive frames (reference snowvision/triangulation.py:4-22,164-186,
+ * called frame after frame by main.py:72-78).  Dense layout: pts (F,P,J,3) in/out, nout (F) persons present,
+ * nsm (F) persons in the smoothed list.  state: [0]=initialised, [1]=n0 (persons of the first frame), then
+ * xp, y, yd as (P,J,3) each.  The first frame passes through and seeds the followers; later frames update
+ * persons k < min(nout, n0) only. */
+int snow_oracle_smooth(int F, int P, int J, double* pts, const int* nout, int* nsm, double f, double z,
+                       double r, double T, double* state) {
+    const double pi = 3.14159265358979323846;
+    const double k1 = z / (pi * f), k2 = 1 / ((2 * pi * f) * (2 * pi * f)), k3 = r * z / (2 * pi * f);
+    const size_t N = (size_t)P * J * 3;
+    double *xp = state + 2, *y = xp + N, *yd = y + N;
+    for (int t = 0; t < F; ++t) {
+        int n = nout[t] < 0 ? 0 : (nout[t] > P ? P : nout[t]);
+        double* x = pts + (size_t)t * N;
+        if (state[0] == 0.0) {
+            for (size_t i = 0; i < (size_t)n * J * 3; ++i) { xp[i] = x[i]; y[i] = x[i]; yd[i] = 0.0; }
+            state[0] = 1.0;
+            state[1] = (double)n;
+            nsm[t] = n;
+            continue;
+        }
+        const int n0 = (int)state[1], m = n < n0 ? n : n0;
+        for (size_t i = 0; i < (size_t)m * J * 3; ++i) {
+            const double xd = (x[i] - xp[i]) / T;
+            xp[i] = x[i];
+            y[i] = y[i] + T * yd[i];
+            yd[i] = yd[i] + T * (x[i] + k3 * xd - y[i] - k1 * yd[i]) / k2;
+            x[i] = y[i];
+        }
+        nsm[t] = m;
+    }
+    return 0;
+}

@@ -2,13 +2,15 @@
 
 Drop-in names (reference ``snowvision.camera`` / ``snowvision.triangulation``):
 ``Camera``, ``CameraGroup``, ``Skew_Ray_Solver``, ``Human_Triangulation``,
-``Human_Triangulation_Condense``.  Batch API: ``TriangulationEngine``, ``triangulate_batch``.
+``Human_Triangulation_Condense``, ``Human_Triangulation_Smooth``.  Batch API: ``TriangulationEngine``,
+``triangulate_batch``, ``SmoothState``.
 Importing the package does not need a GPU; calling into it does (no CPU fallback).
 """
 from .camera import Camera, CameraGroup  # noqa: F401
 
 _LAZY = {"TriangulationEngine": "engine", "triangulate_batch": "engine", "Skew_Ray_Solver": "triangulation",
-         "Human_Triangulation": "triangulation", "Human_Triangulation_Condense": "triangulation"}
+         "Human_Triangulation": "triangulation", "Human_Triangulation_Condense": "triangulation",
+         "Human_Triangulation_Smooth": "triangulation", "SmoothState": "engine"}
 
 
 __all__ = ["Camera", "CameraGroup"] + sorted(_LAZY)   # `from snowmocap_b200 import *` overrides the reference's names

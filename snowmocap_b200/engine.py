@@ -197,6 +197,51 @@ class TriangulationEngine:
         return dist, mid
 
 
+class SmoothState:
+    """Device-resident followers of ``Human_Triangulation_Smooth`` (reference triangulation.py:4-22, 164-186)
+    for one clip: create once, then ``run`` batches of consecutive frames in order."""
+
+    def __init__(self, engine, max_persons, J, f=2.0, z=0.75, r=0.0):
+        self._eng, self._lib, self._s = engine, engine._lib, ct.c_void_p()
+        self.max_persons, self.J = int(max_persons), int(J)
+        with torch.cuda.device(engine.device):
+            _lib.check(self._lib.snowtri_smooth_create(engine._h, ct.byref(self._s), self.max_persons, self.J,
+                                                       float(f), float(z), float(r)), engine._h)
+
+    def reset(self):
+        """The next frame starts a new clip (passes through and seeds the followers)."""
+        _lib.check(self._lib.snowtri_smooth_reset(self._eng._h, self._s, _stream()), self._eng._h)
+
+    def run(self, out, nout, delta_time=1 / 30):
+        """Smooth ``out`` (F,Pout,J,4) float32/float64 cuda tensor in place (x, y, z; score untouched), frames
+        in order.  ``nout`` (F,) int32 persons per frame.  Returns nsmooth (F,) int32: persons in the smoothed
+        list of every frame (first frame of the clip: all of them; later: min(nout, first frame's count))."""
+        if out.dim() != 4 or out.shape[-1] != 4 or not out.is_cuda or not out.is_contiguous():
+            raise ValueError("out must be a contiguous cuda tensor of shape (F,Pout,J,4)")
+        if out.dtype not in (torch.float32, torch.float64):
+            raise ValueError("out must be float32 or float64")
+        F, Pout, J, _ = out.shape
+        if nout.shape != (F,) or nout.dtype != torch.int32 or not nout.is_cuda:
+            raise ValueError("nout must be an int32 cuda tensor of shape (F,)")
+        nsm = torch.empty((F,), dtype=torch.int32, device=out.device)
+        fn = self._lib.snowtri_smooth_run if out.dtype == torch.float32 else self._lib.snowtri_smooth_run_f64
+        with torch.cuda.device(self._eng.device):
+            _lib.check(fn(self._eng._h, self._s, _ptr(out), _ptr(nout), _ptr(nsm), F, Pout, J, float(delta_time),
+                          _stream()), self._eng._h)
+        return nsm
+
+    def close(self):
+        if self._s:
+            self._lib.snowtri_smooth_destroy(self._s)
+            self._s = ct.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def triangulate_batch(kpts, scores, counts, K, R, t, Pout=None, keypoint_num=None, precision="f64", **params):
     """One-shot convenience wrapper: build an engine, run the fused path, return its result dict."""
     eng = TriangulationEngine(K, R, t, device=kpts.device.index or 0, precision=precision, **params)

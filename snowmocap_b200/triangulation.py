@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .engine import TriangulationEngine
+from .engine import SmoothState, TriangulationEngine
 
 POINTS = "hrnet_triangulate_points"
 KSCORES = "hrnet_triangulate_keypoint_scores"
@@ -104,3 +104,53 @@ def Human_Triangulation_Condense(result, condense_distance_tol=0.1, condense_per
         out[KSCORES].append(np.ascontiguousarray(o[i, :, 3]))
         out[PSCORES].append(np.float64(ps[i]))
     return out
+
+
+SODS = "second_order_dynamics"
+
+
+class _Followers:
+    """What this package stores under ``'second_order_dynamics'``: the device-resident followers of one clip
+    (the reference stores a list of lists of ``SecondOrderDynamic`` objects there, triangulation.py:176,184)."""
+
+    def __init__(self, n0, J, f, z, r):
+        self.n0, self.J = n0, J
+        self.state = SmoothState(_util_engine(), max(n0, 1), J, f, z, r) if n0 > 0 and J > 0 else None
+
+    def __len__(self):          # len(previous_result['second_order_dynamics']) == persons of the first frame
+        return self.n0
+
+
+def Human_Triangulation_Smooth(result, previous_result=None, f=2, z=0.75, r=0, delta_time=1 / 30):
+    """Second-order-dynamics smoothing of the 3D joints; reference triangulation.py:164-186 (main.py:72-78).
+
+    First call of a clip (``previous_result`` not a dict): points pass through, followers are created from them.
+    Later calls: persons are zipped by list position with the followers of the FIRST frame (later persons are
+    dropped, absent persons' followers do not advance); scores pass through unaligned, like the reference."""
+    pts = result[POINTS]
+    if not isinstance(previous_result, dict):
+        n0 = len(pts)
+        J = int(np.asarray(pts[0]).shape[0]) if n0 else 0
+        fol = _Followers(n0, J, f, z, r)
+        if fol.state is not None:
+            _smooth_step(fol, pts, delta_time)      # seeds the followers; the frame itself is unchanged
+        return {POINTS: result[POINTS], KSCORES: result[KSCORES], PSCORES: result[PSCORES], SODS: fol}
+    fol = previous_result[SODS]
+    damped = _smooth_step(fol, pts, delta_time) if fol.state is not None else []
+    return {POINTS: damped, KSCORES: result[KSCORES], PSCORES: result[PSCORES], SODS: fol}
+
+
+def _smooth_step(fol, pts, delta_time):
+    n = len(pts)
+    if n == 0:
+        # no person in this frame: nothing to update (the reference's zip is empty)
+        return []
+    J = fol.J
+    dev = fol.state._eng.device
+    buf = np.zeros((1, n, J, 4), np.float64)
+    buf[0, :, :, :3] = np.asarray(pts, np.float64).reshape(n, -1, 3)[:, :J]
+    out = torch.from_numpy(buf).to(dev)
+    nsm = fol.state.run(out, torch.tensor([n], dtype=torch.int32, device=dev), delta_time)
+    m = int(nsm.cpu()[0])
+    o = out[0, :m, :, :3].cpu().numpy()
+    return [np.ascontiguousarray(o[i]) for i in range(m)]

@@ -94,6 +94,29 @@ def floor_rig():
                      [np.array(c["t"]).reshape(3) for c in info])
 
 
+def save_smooth_case(name, counts, J, f, z, r, dt, seed):
+    """Human_Triangulation_Smooth of the real reference, frame after frame like main.py:72-78, on a synthetic
+    walk of persons with a varying person count per frame."""
+    rng = np.random.default_rng(seed)
+    F, P = len(counts), max(max(counts), 1)
+    base = rng.uniform(-2, 2, (P, 1, 3)) + rng.uniform(-0.4, 0.4, (P, J, 3))
+    walk = np.cumsum(rng.normal(0, 0.01, (F, P, J, 3)), axis=0)
+    pts = (base[None] + walk + rng.normal(0, 0.004, (F, P, J, 3))).astype(np.float32).astype(np.float64)
+    prev, d = None, {}
+    for t in range(F):
+        n = counts[t]
+        res = {"hrnet_triangulate_points": [pts[t, k].copy() for k in range(n)],
+               "hrnet_triangulate_keypoint_scores": [np.ones(J) for _ in range(n)],
+               "hrnet_triangulate_person_scores": [1.0] * n}
+        res = ref.Human_Triangulation_Smooth(res, prev, f=f, z=z, r=r, delta_time=dt)
+        prev = res
+        out = res["hrnet_triangulate_points"]
+        d[f"out_{t}"] = np.array(out, np.float64).reshape(len(out), J, 3)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), pts=pts, counts=np.array(counts, np.int32),
+                        params=json.dumps(dict(f=f, z=z, r=r, dt=dt)), **d)
+    print(f"{name}: frames={F} persons in={counts} out={[d[f'out_{t}'].shape[0] for t in range(F)]}")
+
+
 def main():
     floor = floor_rig()
     np.savez(os.path.join(HERE, "floor_rig.npz"), K=floor.K, R=floor.R, t=floor.t)
@@ -125,6 +148,11 @@ def main():
     save_case("quirk_scoretol", ring4, dq, dict(M, ast=0.0, score_tol=0.08, cond_tol=0.5))
     save_case("quirk_truncate", ring4, dq, dict(M, ast=0.1, center=3), keypoint_num=11)
     save_case("quirk_bigtol", ring4, dq, dict(M, ast=0.05, cond_tol=10.0))
+    # temporal smoothing: shipped parameters (configs/snowmocap_default_config.json:18-21),
+    # a person count that grows, shrinks and hits zero; non-zero r; a clip whose first frame is empty
+    save_smooth_case("smooth_default", [2, 2, 3, 3, 1, 2, 0, 2, 2, 1, 3, 2] + [2] * 28, 17, 2.5, 0.75, 0, 0.03333333333, 21)
+    save_smooth_case("smooth_r", [1] * 30, 133, 2.0, 0.75, 0.5, 1 / 30, 22)
+    save_smooth_case("smooth_emptyfirst", [0, 2, 2, 1, 2], 17, 2.5, 0.75, 0, 1 / 30, 23)
 
 
 if __name__ == "__main__":

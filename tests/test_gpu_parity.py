@@ -372,3 +372,92 @@ def test_error_behaviour(torch_cuda):
            "hrnet_triangulate_keypoint_scores": [np.ones(17)] * 3, "hrnet_triangulate_person_scores": [1.0] * 3}
     with pytest.raises(IndexError):
         sv.Human_Triangulation_Condense(tri, keypoint_num=30)
+
+
+# ---- temporal smoothing -----------------------------------------------------------------
+from conftest import GOLDEN, smooth_golden_names  # noqa: E402
+
+
+def _smooth_golden(name):
+    import json
+    import os
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    counts = z["counts"]
+    return z["pts"], counts, json.loads(str(z["params"])), [z[f"out_{t}"] for t in range(len(counts))]
+
+
+@pytest.mark.parametrize("name", smooth_golden_names())
+def test_smooth_dropin_matches_reference_golden(torch_cuda, name):
+    """main.py:72-78 call pattern through the drop-in name, frame after frame."""
+    import snowmocap_b200 as sv
+    pts, counts, prm, want = _smooth_golden(name)
+    J = pts.shape[2]
+    prev = None
+    for t in range(len(counts)):
+        n = int(counts[t])
+        res = {"hrnet_triangulate_points": [pts[t, k].copy() for k in range(n)],
+               "hrnet_triangulate_keypoint_scores": [np.ones(J) for _ in range(n)],
+               "hrnet_triangulate_person_scores": [1.0] * n}
+        res = sv.Human_Triangulation_Smooth(res, prev, f=prm["f"], z=prm["z"], r=prm["r"], delta_time=prm["dt"])
+        prev = res
+        got = res["hrnet_triangulate_points"]
+        assert set(res) == {"hrnet_triangulate_points", "hrnet_triangulate_keypoint_scores",
+                            "hrnet_triangulate_person_scores", "second_order_dynamics"}
+        assert len(got) == want[t].shape[0], f"frame {t}"
+        assert len(res["hrnet_triangulate_keypoint_scores"]) == n      # scores pass through unaligned
+        if want[t].size:
+            np.testing.assert_allclose(np.array(got), want[t], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", smooth_golden_names())
+@pytest.mark.parametrize("split", [None, 1, 6])
+def test_smooth_batch_matches_reference_golden(torch_cuda, name, split):
+    """Whole clip (or streamed chunks) through snowtri_smooth_run_f64."""
+    torch = torch_cuda
+    from snowmocap_b200.engine import SmoothState
+    import snowmocap_b200 as sv
+    pts, counts, prm, want = _smooth_golden(name)
+    F, P, J, _ = pts.shape
+    eng = sv.triangulation._util_engine()
+    st = SmoothState(eng, P, J, prm["f"], prm["z"], prm["r"])
+    dense = np.zeros((F, P, J, 4))
+    dense[..., :3] = pts
+    dense[..., 3] = 0.25
+    step = F if split is None else split
+    for t0 in range(0, F, step):
+        out = torch.from_numpy(dense[t0:t0 + step].copy()).cuda()
+        nsm = st.run(out, torch.from_numpy(counts[t0:t0 + step].copy()).cuda(), prm["dt"]).cpu().numpy()
+        o = out.cpu().numpy()
+        for i, t in enumerate(range(t0, min(F, t0 + step))):
+            assert nsm[i] == want[t].shape[0], f"frame {t}"
+            if want[t].size:
+                np.testing.assert_allclose(o[i, :nsm[i], :, :3], want[t], rtol=1e-11, atol=1e-13)
+            assert np.all(o[i, :, :, 3] == 0.25)                                  # score untouched
+            np.testing.assert_array_equal(o[i, nsm[i]:, :, :3], pts[t, nsm[i]:])   # dropped persons untouched
+
+
+def test_smooth_float32_layout_long_clip_vs_c_oracle(torch_cuda):
+    """snowtri_run layout (float32 x,y,z,score) over a long clip with a ragged person count."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    from snowmocap_b200.engine import SmoothState
+    import snowmocap_b200 as sv
+    rng = np.random.default_rng(5)
+    F, P, J = 5000, 3, 133
+    pts = (rng.uniform(-2, 2, (1, P, 1, 3)) + np.cumsum(rng.normal(0, 0.01, (F, P, J, 3)), axis=0)).astype(np.float32)
+    nout = rng.integers(0, P + 1, F).astype(np.int32)
+    nout[0] = 2
+    ref, nsm_ref, _ = c_oracle.smooth(pts.astype(np.float64), nout, 2.5, 0.75, 0.3, 1 / 30)
+    dense = np.zeros((F, P, J, 4), np.float32)
+    dense[..., :3] = pts
+    st = SmoothState(sv.triangulation._util_engine(), P, J, 2.5, 0.75, 0.3)
+    out = torch.from_numpy(dense).cuda()
+    nsm = st.run(out, torch.from_numpy(nout).cuda(), 1 / 30).cpu().numpy()
+    assert np.array_equal(nsm, nsm_ref)
+    o = out.cpu().numpy()
+    m = np.arange(P)[None, :] < nsm[:, None]
+    assert rel_l2(o[m][..., :3], ref[m]) < 1e-6          # float32 storage of the result
+    st.reset()
+    out2 = torch.from_numpy(dense).cuda()
+    nsm2 = st.run(out2, torch.from_numpy(nout).cuda(), 1 / 30).cpu().numpy()
+    assert np.array_equal(nsm2, nsm) and torch.equal(out2, out)   # reset starts the same clip again

@@ -1,4 +1,6 @@
 """Pin both CPU oracles to the golden vectors produced by the real reference (CPU only)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -93,3 +95,47 @@ def test_noise_free_input_gives_nan_like_reference():
     hs = loop_oracle.back_project(rig.K[1], rig.R[1], uv[1, 0, 0])
     dist, _ = loop_oracle.skew_ray_solve(hm, hs, rig.t[0].reshape(3, 1), rig.t[1].reshape(3, 1))
     assert dist < 1e-12
+
+
+# ---- temporal smoothing: both restatements against the real reference's outputs ----
+from conftest import GOLDEN, smooth_golden_names  # noqa: E402
+
+
+def _smooth_golden(name):
+    import json
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    counts = z["counts"]
+    return z["pts"], counts, json.loads(str(z["params"])), [z[f"out_{t}"] for t in range(len(counts))]
+
+
+@pytest.mark.parametrize("name", smooth_golden_names())
+def test_loop_oracle_smooth_matches_reference(name):
+    from oracle import loop_oracle
+    pts, counts, prm, want = _smooth_golden(name)
+    got = loop_oracle.smooth_sequence([[pts[t, k] for k in range(counts[t])] for t in range(len(counts))],
+                                      f=prm["f"], z=prm["z"], r=prm["r"], delta_time=prm["dt"])
+    for t, (g, w) in enumerate(zip(got, want)):
+        assert g.shape[0] == w.shape[0], f"frame {t}"
+        if w.size:
+            np.testing.assert_allclose(g, w, rtol=1e-13, atol=1e-15)
+
+
+@pytest.mark.parametrize("name", smooth_golden_names())
+@pytest.mark.parametrize("split", [None, 1, 7])
+def test_c_oracle_smooth_matches_reference(name, split):
+    """Dense C restatement, also fed in chunks with the state carried over (streaming a clip)."""
+    from oracle import c_oracle
+    pts, counts, prm, want = _smooth_golden(name)
+    F = len(counts)
+    step = F if split is None else split
+    state, outs, nsm = None, [], []
+    for t0 in range(0, F, step):
+        o, n, state = c_oracle.smooth(pts[t0:t0 + step], counts[t0:t0 + step], prm["f"], prm["z"], prm["r"],
+                                      prm["dt"], state=state)
+        outs.append(o)
+        nsm.append(n)
+    out, nsm = np.concatenate(outs), np.concatenate(nsm)
+    for t, w in enumerate(want):
+        assert nsm[t] == w.shape[0], f"frame {t}"
+        if w.size:
+            np.testing.assert_allclose(out[t, :nsm[t]], w, rtol=1e-12, atol=1e-14)
