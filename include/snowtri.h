@@ -128,11 +128,15 @@ int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs
  *              fixes n0 = its person count; later frames give min(nout, n0) -- the reference zips persons
  *              with the followers created on the first frame, so later persons are dropped and followers of
  *              absent persons are not advanced.  Slots >= d_nsmooth[f] are left untouched.
- * The frame loop is sequential inside one launch (the recurrence is); max_persons bounds n0. */
+ * Batches of up to 256 frames run in one launch with a sequential frame loop (the recurrence is sequential);
+ * longer batches are cut into 128-frame chunks that run in parallel, with the state handed from chunk to
+ * chunk through powers of the (affine) update matrix -- snowtri_smooth_set_chunked(s, 0) forces the
+ * sequential kernel.  max_persons bounds n0. */
 typedef struct snowtri_smooth_state snowtri_smooth_t;
 int snowtri_smooth_create(snowtri_t* h, snowtri_smooth_t** out, int max_persons, int J, double f, double z, double r);
 int snowtri_smooth_destroy(snowtri_smooth_t* s);
 int snowtri_smooth_reset(snowtri_t* h, snowtri_smooth_t* s, void* stream);   /* next frame starts a new clip */
+int snowtri_smooth_set_chunked(snowtri_smooth_t* s, int enabled);
 int snowtri_smooth_run(snowtri_t* h, snowtri_smooth_t* s, float* d_out, const int* d_nout, int* d_nsmooth,
                        int F, int Pout, int J, double delta_time, void* stream);
 int snowtri_smooth_run_f64(snowtri_t* h, snowtri_smooth_t* s, double* d_out, const int* d_nout, int* d_nsmooth,

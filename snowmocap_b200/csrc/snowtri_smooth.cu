@@ -11,6 +11,17 @@
 // position, so persons beyond that count are dropped (nsm = min(nout, n0)) and followers of absent persons
 // are not advanced; scores pass through untouched.
 //
+// Long batches are cut into chunks of kChunk frames that run in parallel (the update of a present frame is
+// affine in the state (xp, y, yd): s' = A s + b x):
+//   pass A  every (chunk, person, joint) runs the recurrence over its chunk from a ZERO state -> b_c, and
+//           counts the frames n_c in which its person was present;
+//   pass B  per (person, joint), sequentially over the chunks: start_c+1 = A^n_c start_c + b_c (A^n from a
+//           table computed on the host);
+//   pass C  every (chunk, person, joint) runs the recurrence again from its true start state and writes the
+//           smoothed points.
+// Inside a chunk the arithmetic is the reference's sequential recurrence; only the hand-over between chunks
+// is evaluated differently (agreement with the sequential kernel ~1e-15 relative).
+//
 // Arithmetic: float64 like the reference.  (x - xp)/T and (...)/k2 are evaluated as multiplications by the
 // reciprocals computed once on the host (1 ulp per step away from a true division, damped by the filter).
 #include <math.h>
@@ -23,6 +34,13 @@ struct snowtri_smooth_state {
     int device, P, J;
     double f, z, r;
     double* d_state;  // [0] initialised, [1] n0, then xp, y, yd as (P, J, 3) each
+    // chunk-parallel path
+    double* d_work;   // per chunk: b (P,J,9) then start (P,J,9)
+    int* d_cnt;       // per chunk: present-frame count per person (P), then a "seeded here" flag
+    double* d_apow;   // (kChunk+1, 9) powers of the state matrix for the current delta_time
+    size_t work_chunks;
+    double apow_T;
+    int sequential;   // 1 = always the single-launch sequential kernel
 };
 
 namespace snowtri {
@@ -125,6 +143,170 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
     }
 }
 
+
+constexpr int kChunk = 128;  // frames per chunk of the parallel path
+
+// One frame of one (person, joint): the reference's update (triangulation.py:15-22) on the three axes.
+__device__ __forceinline__ void follower_step(const SmoothArgs& a, const double* x, double* xp, double* y, double* yd) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const double xd = (x[c] - xp[c]) * a.invT;
+        xp[c] = x[c];
+        y[c] = y[c] + a.T * yd[c];
+        yd[c] = yd[c] + a.T * (x[c] + a.k3 * xd - y[c] - a.k1 * yd[c]) * a.inv_k2;
+    }
+}
+
+struct ChunkArgs {
+    SmoothArgs s;
+    double* work;  // per chunk: b (P*J*9), start (P*J*9)
+    int* cnt;      // per chunk: P counts + 1 seeded flag
+    const double* apow;
+    int nchunks;
+};
+
+// PASS 0: pass A (from a zero state, no output)   PASS 2: pass C (from the true start state, writes)
+template <typename V, int PASS>
+__global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
+    const SmoothArgs& a = ca.s;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = tid / a.J, j = tid - k * a.J;
+    if (k >= a.P) return;
+    const int chunk = blockIdx.y;
+    const int t_begin = chunk * kChunk, t_end = min(a.F, t_begin + kChunk);
+    const bool was_init = a.state[0] != 0.0;
+    const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
+    const size_t ch = (size_t)k * a.J + j, nch = (size_t)a.P * a.J;
+    double* wb = ca.work + (size_t)chunk * nch * 18 + ch * 9;
+    double xp[3] = {0, 0, 0}, y[3] = {0, 0, 0}, yd[3] = {0, 0, 0};
+    if (PASS == 2) {
+        const double* ws = wb + nch * 9;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            xp[c] = ws[c];
+            y[c] = ws[3 + c];
+            yd[c] = ws[6 + c];
+        }
+    }
+    V* pts = reinterpret_cast<V*>(a.pts);
+    const size_t stride = (size_t)a.Pout * a.J;
+    const bool inrange = k < a.Pout;
+    const size_t base = (size_t)(inrange ? k : 0) * a.J + j;
+    int present = 0;
+    V buf[kSmoothAhead];
+    int nb[kSmoothAhead];
+#pragma unroll
+    for (int u = 0; u < kSmoothAhead; ++u)
+        if (t_begin + u < t_end) {
+            buf[u] = pts[(size_t)(t_begin + u) * stride + base];
+            nb[u] = a.nout[t_begin + u];
+        }
+    for (int t0 = t_begin; t0 < t_end; t0 += kSmoothAhead) {
+#pragma unroll
+        for (int u = 0; u < kSmoothAhead; ++u) {
+            const int t = t0 + u;
+            if (t >= t_end) break;
+            const V p = buf[u];
+            const int n = min(max(nb[u], 0), a.Pout);
+            if (t + kSmoothAhead < t_end) {
+                buf[u] = pts[(size_t)(t + kSmoothAhead) * stride + base];
+                nb[u] = a.nout[t + kSmoothAhead];
+            }
+            const double x[3] = {(double)p.x, (double)p.y, (double)p.z};
+            if (!was_init && t == 0) {  // first frame of the clip: seed, pass through (reference :177-184)
+                if (k < n0) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        xp[c] = y[c] = x[c];
+                        yd[c] = 0.0;
+                    }
+                }
+                if (PASS == 2 && tid == 0) a.nsm[t] = n;
+                continue;
+            }
+            const int m = min(n, n0);
+            if (PASS == 2 && tid == 0) a.nsm[t] = m;
+            if (k < m) {
+                follower_step(a, x, xp, y, yd);
+                ++present;
+                if (PASS == 2) {
+                    V o = p;
+                    o.x = (decltype(o.x))y[0];
+                    o.y = (decltype(o.y))y[1];
+                    o.z = (decltype(o.z))y[2];
+                    pts[(size_t)t * stride + base] = o;
+                }
+            }
+        }
+    }
+    if (PASS == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            wb[c] = xp[c];
+            wb[3 + c] = y[c];
+            wb[6 + c] = yd[c];
+        }
+        if (j == 0) ca.cnt[(size_t)chunk * (a.P + 1) + k] = present;
+        if (tid == 0) ca.cnt[(size_t)chunk * (a.P + 1) + a.P] = (!was_init && chunk == 0) ? 1 : 0;
+    }
+}
+
+// Pass B: per (person, joint), hand the state from chunk to chunk; finally store it for the next call.
+__global__ void __launch_bounds__(128) smooth_carry_kernel(const ChunkArgs ca) {
+    const SmoothArgs& a = ca.s;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = tid / a.J, j = tid - k * a.J;
+    if (k >= a.P) return;
+    const size_t ch = (size_t)k * a.J + j, nch = (size_t)a.P * a.J, N = nch * 3;
+    double* sxp = a.state + 2 + ch * 3;
+    double* sy = sxp + N;
+    double* syd = sy + N;
+    const bool was_init = a.state[0] != 0.0;
+    const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
+    double s[9];  // xp[3], y[3], yd[3]
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        s[c] = sxp[c];
+        s[3 + c] = sy[c];
+        s[6 + c] = syd[c];
+    }
+    for (int chunk = 0; chunk < ca.nchunks; ++chunk) {
+        double* wb = ca.work + (size_t)chunk * nch * 18 + ch * 9;
+        double* ws = wb + nch * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) ws[i] = s[i];
+        const int n = ca.cnt[(size_t)chunk * (a.P + 1) + k];
+        const bool seeded = ca.cnt[(size_t)chunk * (a.P + 1) + a.P] != 0 && k < n0;
+        const double* A = ca.apow + (size_t)n * 9;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double v0 = s[c], v1 = s[3 + c], v2 = s[6 + c];  // (xp, y, yd) of axis c
+            double r0 = wb[c], r1 = wb[3 + c], r2 = wb[6 + c];
+            if (!seeded) {  // a seeded chunk ignores the incoming state
+                r0 += A[0] * v0 + A[1] * v1 + A[2] * v2;
+                r1 += A[3] * v0 + A[4] * v1 + A[5] * v2;
+                r2 += A[6] * v0 + A[7] * v1 + A[8] * v2;
+            }
+            s[c] = r0;
+            s[3 + c] = r1;
+            s[6 + c] = r2;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        sxp[c] = s[c];
+        sy[c] = s[3 + c];
+        syd[c] = s[6 + c];
+    }
+}
+
+__global__ void smooth_finish_kernel(double* state, const int* nout, int Pout, int P) {
+    if (state[0] == 0.0) {
+        state[1] = (double)min(min(max(nout[0], 0), Pout), P);
+        state[0] = 1.0;
+    }
+}
+
 }  // namespace snowtri
 
 using namespace snowtri;
@@ -155,7 +337,16 @@ extern "C" int snowtri_smooth_destroy(snowtri_smooth_t* s) {
     if (!s) return SNOWTRI_OK;
     cudaSetDevice(s->device);
     if (s->d_state) cudaFree(s->d_state);
+    if (s->d_work) cudaFree(s->d_work);
+    if (s->d_cnt) cudaFree(s->d_cnt);
+    if (s->d_apow) cudaFree(s->d_apow);
     free(s);
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_smooth_set_chunked(snowtri_smooth_t* s, int enabled) {
+    if (!s) return SNOWTRI_E_ARG;
+    s->sequential = enabled ? 0 : 1;
     return SNOWTRI_OK;
 }
 
@@ -186,10 +377,55 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
     a.inv_k2 = 1.0 / k2;
     a.k3 = s->r * s->z / (2 * pi * s->f);                               // :9
     const int threads = s->P * J, grid = (threads + 127) / 128;
-    if (f64) smooth_kernel<double4><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
-    else smooth_kernel<float4><<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (F <= 2 * kChunk || s->sequential) {  // short batch: one sequential launch
+        if (f64) smooth_kernel<double4><<<grid, 128, 0, st>>>(a);
+        else smooth_kernel<float4><<<grid, 128, 0, st>>>(a);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+        return SNOWTRI_OK;
+    }
+    // chunk-parallel path
+    const int nchunks = (F + kChunk - 1) / kChunk;
+    const size_t nch = (size_t)s->P * J;
+    if (s->work_chunks < (size_t)nchunks) {
+        if (s->d_work) cudaFree(s->d_work);
+        if (s->d_cnt) cudaFree(s->d_cnt);
+        s->d_work = nullptr; s->d_cnt = nullptr; s->work_chunks = 0;
+        CUDA_TRY(h, cudaMalloc(&s->d_work, (size_t)nchunks * nch * 18 * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&s->d_cnt, (size_t)nchunks * (s->P + 1) * sizeof(int)));
+        s->work_chunks = (size_t)nchunks;
+    }
+    if (!s->d_apow || s->apow_T != delta_time) {
+        // state matrix of one present frame, (xp, y, yd)' = A (xp, y, yd) + b x, and its powers
+        if (!s->d_apow) CUDA_TRY(h, cudaMalloc(&s->d_apow, (size_t)(kChunk + 1) * 9 * sizeof(double)));
+        const double T = delta_time, g = T / k2;
+        const double A[9] = {0, 0, 0, 0, 1, T, -a.k3 / k2, -g, 1 - g * (T + a.k1)};
+        static double pw[(kChunk + 1) * 9];
+        const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+        memcpy(pw, I, sizeof(I));
+        for (int n = 1; n <= kChunk; ++n)
+            for (int r_ = 0; r_ < 3; ++r_)
+                for (int c_ = 0; c_ < 3; ++c_) {
+                    double v = 0;
+                    for (int m_ = 0; m_ < 3; ++m_) v += A[r_ * 3 + m_] * pw[(n - 1) * 9 + m_ * 3 + c_];
+                    pw[n * 9 + r_ * 3 + c_] = v;
+                }
+        CUDA_TRY(h, cudaMemcpyAsync(s->d_apow, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));  // pw is a host static: do not let a later call overwrite it in flight
+        s->apow_T = delta_time;
+    }
+    ChunkArgs ca;
+    ca.s = a; ca.work = s->d_work; ca.cnt = s->d_cnt; ca.apow = s->d_apow; ca.nchunks = nchunks;
+    const dim3 g2(grid, nchunks);
+    if (f64) smooth_chunk_kernel<double4, 0><<<g2, 128, 0, st>>>(ca);
+    else smooth_chunk_kernel<float4, 0><<<g2, 128, 0, st>>>(ca);
+    smooth_carry_kernel<<<grid, 128, 0, st>>>(ca);
+    if (f64) smooth_chunk_kernel<double4, 2><<<g2, 128, 0, st>>>(ca);
+    else smooth_chunk_kernel<float4, 2><<<g2, 128, 0, st>>>(ca);
+    smooth_finish_kernel<<<1, 1, 0, st>>>(s->d_state, d_nout, Pout, s->P);
     CUDA_TRY(h, cudaGetLastError());
-    h->launches += 1;
+    h->launches += 4;
     return SNOWTRI_OK;
 }
 

@@ -461,3 +461,34 @@ def test_smooth_float32_layout_long_clip_vs_c_oracle(torch_cuda):
     out2 = torch.from_numpy(dense).cuda()
     nsm2 = st.run(out2, torch.from_numpy(nout).cuda(), 1 / 30).cpu().numpy()
     assert np.array_equal(nsm2, nsm) and torch.equal(out2, out)   # reset starts the same clip again
+
+
+@pytest.mark.parametrize("chunked", [True, False])
+@pytest.mark.parametrize("batches", [(3000,), (1, 700, 299, 2000), (300, 2700)])
+def test_smooth_long_clip_float64_vs_c_oracle(torch_cuda, chunked, batches):
+    """Chunk-parallel and sequential kernels, whole clip or streamed batches, ragged person count."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    from snowmocap_b200.engine import SmoothState
+    import snowmocap_b200 as sv
+    rng = np.random.default_rng(8)
+    F, P, J = sum(batches), 3, 17
+    pts = rng.uniform(-2, 2, (1, P, 1, 3)) + np.cumsum(rng.normal(0, 0.01, (F, P, J, 3)), axis=0)
+    nout = rng.integers(0, P + 2, F).astype(np.int32)      # sometimes more persons than slots
+    nout[0] = 2
+    ref, nsm_ref, _ = c_oracle.smooth(pts, np.minimum(nout, P), 2.5, 0.75, 0.4, 0.03333333333)
+    st = SmoothState(sv.triangulation._util_engine(), P, J, 2.5, 0.75, 0.4)
+    st.set_chunked(chunked)
+    dense = np.zeros((F, P, J, 4))
+    dense[..., :3] = pts
+    t0, got, nsm = 0, [], []
+    for b in batches:
+        out = torch.from_numpy(dense[t0:t0 + b].copy()).cuda()
+        nsm.append(st.run(out, torch.from_numpy(nout[t0:t0 + b].copy()).cuda(), 0.03333333333).cpu().numpy())
+        got.append(out.cpu().numpy())
+        t0 += b
+    got, nsm = np.concatenate(got), np.concatenate(nsm)
+    assert np.array_equal(nsm, nsm_ref)
+    m = np.arange(P)[None, :] < nsm[:, None]
+    np.testing.assert_allclose(got[m][..., :3], ref[m], rtol=1e-10, atol=1e-12)
+    np.testing.assert_array_equal(got[~m][..., :3], pts[~m])
