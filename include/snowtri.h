@@ -142,6 +142,17 @@ int snowtri_smooth_run(snowtri_t* h, snowtri_smooth_t* s, float* d_out, const in
 int snowtri_smooth_run_f64(snowtri_t* h, snowtri_smooth_t* s, double* d_out, const int* d_nout, int* d_nsmooth,
                            int F, int Pout, int J, double delta_time, void* stream);
 
+/* Ragged ingestion: what main.py:50-55 + add_human_2D_points/clear_2D_points (reference
+ * snowvision/camera.py:234-261) do per frame, for a whole clip on the device.  The detector's outputs of every
+ * (frame, camera) -- (N_fc, J, 2) keypoints and (N_fc, J) scores, persons in detector order -- are
+ * concatenated in (frame, camera) order:
+ *   d_det_kpts (M, J, 2) float32, d_det_scores (M, J) float32, d_offsets (F*C + 1) int64 CSR row starts
+ * and padded into the dense layout snowtri_run consumes: d_kpts (F,C,P,J,2), d_scores (F,C,P,J) (unused slots
+ * zeroed), d_counts (F,C) = min(N_fc, P).  Persons beyond the P slots of a camera are dropped. */
+int snowtri_pack_ragged(snowtri_t* h, const float* d_det_kpts, const float* d_det_scores,
+                        const long long* d_offsets, int F, int P, int J,
+                        float* d_kpts, float* d_scores, int* d_counts, void* stream);
+
 /* Introspection. */
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */

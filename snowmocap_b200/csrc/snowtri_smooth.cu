@@ -438,3 +438,53 @@ extern "C" int snowtri_smooth_run_f64(snowtri_t* h, snowtri_smooth_t* s, double*
                                       int* d_nsmooth, int F, int Pout, int J, double delta_time, void* stream) {
     return smooth_run(h, s, d_out, true, d_nout, d_nsmooth, F, Pout, J, delta_time, stream);
 }
+
+
+// ---- ragged ingestion ---------------------------------------------------------------------
+// What main.py:50-55 does per frame and camera -- `for person, score in zip(keypoints, scores):
+// add_human_2D_points(person, score, camera_index)` -- for a whole clip: the detector's outputs
+// (N_fc, J, 2) / (N_fc, J) of every (frame, camera) are concatenated in (frame, camera, detector order) and
+// described by CSR offsets; this kernel pads them into the dense batch layout of snowtri_run.
+namespace snowtri {
+__global__ void __launch_bounds__(256) pack_ragged_kernel(const float2* __restrict__ det_kpts, const float* __restrict__ det_scores,
+                                                          const long long* __restrict__ offsets, int FC, int P, int J,
+                                                          float2* __restrict__ kpts, float* __restrict__ scores,
+                                                          int* __restrict__ counts) {
+    // one warp per (frame, camera, person slot) row of J joints
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= (long long)FC * P) return;
+    const int fc = (int)(row / P), p = (int)(row - (long long)fc * P);
+    const long long o0 = offsets[fc], n = offsets[fc + 1] - o0;
+    if (p == 0 && lane == 0) counts[fc] = (int)(n < 0 ? 0 : (n > P ? P : n));  // persons beyond P slots are dropped
+    const bool have = p < n;
+    const float2* src = det_kpts + (o0 + p) * J;
+    const float* ssrc = det_scores + (o0 + p) * J;
+    float2* dst = kpts + row * J;
+    float* sdst = scores + row * J;
+    for (int j = lane; j < J; j += 32) {
+        dst[j] = have ? src[j] : make_float2(0.f, 0.f);
+        sdst[j] = have ? ssrc[j] : 0.f;
+    }
+}
+}  // namespace snowtri
+
+extern "C" int snowtri_pack_ragged(snowtri_t* h, const float* d_det_kpts, const float* d_det_scores,
+                                   const long long* d_offsets, int F, int P, int J, float* d_kpts, float* d_scores,
+                                   int* d_counts, void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_pack_ragged: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if (!d_offsets || !d_kpts || !d_scores || !d_counts || F < 0 || P < 1 || J < 1)
+        return fail(h, SNOWTRI_E_ARG, "snowtri_pack_ragged: bad argument");
+    if ((((uintptr_t)d_det_kpts | (uintptr_t)d_kpts) & 7u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_pack_ragged: misaligned keypoints");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long rows = (long long)F * h->C * P;
+    const long long blocks = (rows + 7) / 8;
+    if (blocks > 2147483647LL) return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_pack_ragged: batch too large");
+    pack_ragged_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(d_det_kpts), d_det_scores, d_offsets, F * h->C, P, J,
+        reinterpret_cast<float2*>(d_kpts), d_scores, d_counts);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return SNOWTRI_OK;
+}

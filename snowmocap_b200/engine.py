@@ -134,6 +134,44 @@ class TriangulationEngine:
                        self._h)
         return out
 
+    # -- ragged ingestion -----------------------------------------------------------------
+    def pack_detections(self, detections, P=None):
+        """Detector outputs of a clip -> dense device batch.  ``detections[f][c]`` is the pair
+        ``(keypoints (N,J,2), scores (N,J))`` the reference's ``main.py:53`` gets for frame f, camera c
+        (N may be 0).  One concatenate per array on the host, one copy, one kernel; no per-keypoint loop.
+        Returns (kpts (F,C,P,J,2), scores (F,C,P,J), counts (F,C)) cuda tensors; P defaults to the largest N."""
+        F, C = len(detections), self.C
+        ks, ss, ns = [], [], []
+        for frame in detections:
+            if len(frame) != C:
+                raise ValueError(f"every frame needs {C} cameras")
+            for k, s in frame:
+                k = np.asarray(k, np.float32)
+                s = np.asarray(s, np.float32)
+                ns.append(k.shape[0])
+                if k.shape[0]:
+                    ks.append(k.reshape(k.shape[0], -1, 2))
+                    ss.append(s.reshape(s.shape[0], -1))
+        if not ks:
+            raise ValueError("no detections in the clip")
+        det_k, det_s = np.concatenate(ks), np.concatenate(ss)
+        J = det_k.shape[1]
+        if det_s.shape != det_k.shape[:2]:
+            raise ValueError("scores and keypoints disagree")
+        offsets = np.zeros(F * C + 1, np.int64)
+        np.cumsum(ns, out=offsets[1:])
+        P = int(max(ns)) if P is None else int(P)
+        dev = self.device
+        dk, ds = torch.from_numpy(det_k).to(dev), torch.from_numpy(det_s).to(dev)
+        do = torch.from_numpy(offsets).to(dev)
+        kpts = torch.empty((F, C, P, J, 2), dtype=torch.float32, device=dev)
+        scores = torch.empty((F, C, P, J), dtype=torch.float32, device=dev)
+        counts = torch.empty((F, C), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self._lib.snowtri_pack_ragged(self._h, _ptr(dk), _ptr(ds), _ptr(do), F, P, J, _ptr(kpts),
+                                                     _ptr(scores), _ptr(counts), _stream()), self._h)
+        return kpts, scores, counts
+
     def run_host(self, kpts, scores, counts=None, Pout=None, keypoint_num=None, out=None):
         """Fused path through HOST numpy buffers (H2D + kernel + D2H inside the C call, synchronous)."""
         kpts = np.ascontiguousarray(kpts, np.float32)

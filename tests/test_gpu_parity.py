@@ -492,3 +492,41 @@ def test_smooth_long_clip_float64_vs_c_oracle(torch_cuda, chunked, batches):
     m = np.arange(P)[None, :] < nsm[:, None]
     np.testing.assert_allclose(got[m][..., :3], ref[m], rtol=1e-10, atol=1e-12)
     np.testing.assert_array_equal(got[~m][..., :3], pts[~m])
+
+
+# ---- ragged ingestion ---------------------------------------------------------------------
+@pytest.mark.parametrize("P", [None, 2])
+def test_pack_detections_equals_reference_call_sequence(torch_cuda, P):
+    """Ragged detector outputs -> dense batch on the device == what add_human_2D_points builds frame by frame,
+    and the fused path on it == the loop oracle fed the same lists (persons beyond P slots are dropped)."""
+    torch = torch_cuda
+    from oracle import loop_oracle
+    rng = np.random.default_rng(3)
+    rig = synth.ring_rig(5)
+    F, J, Pmax = 9, 17, 3
+    d = synth.make_frames(rig, F, Pmax, J, seed=31, drop_prob=0.4)
+    dets = [[(d["kpts"][f, c, :d["counts"][f, c]], d["scores"][f, c, :d["counts"][f, c]]) for c in range(rig.C)]
+            for f in range(F)]
+    prm = synth.MULTI_PARAMS
+    eng = _engine(rig, prm)
+    kp, sc, cn = eng.pack_detections(dets, P=P)
+    torch.cuda.synchronize()
+    Pd = Pmax if P is None else P
+    want_counts = np.minimum(d["counts"], Pd)
+    assert np.array_equal(cn.cpu().numpy(), want_counts)
+    want_k = np.zeros((F, rig.C, Pd, J, 2), np.float32)
+    want_s = np.zeros((F, rig.C, Pd, J), np.float32)
+    for f in range(F):
+        for c in range(rig.C):
+            n = want_counts[f, c]
+            want_k[f, c, :n], want_s[f, c, :n] = d["kpts"][f, c, :n], d["scores"][f, c, :n]
+    assert np.array_equal(kp.cpu().numpy(), want_k) and np.array_equal(sc.cpu().numpy(), want_s)
+    res = eng.run(kp, sc, cn, Pout=8)
+    torch.cuda.synchronize()
+    out, nout = res["out"].cpu().numpy(), res["nout"].cpu().numpy()
+    for f in range(F):
+        ref = loop_oracle.fused_frame(want_k[f], want_s[f], want_counts[f], rig.K, rig.R, rig.t, prm)
+        n = len(ref["hrnet_triangulate_points"])
+        assert nout[f] == n
+        if n:
+            assert rel_l2(out[f, :n, :, :3], np.array(ref["hrnet_triangulate_points"])) < TOL_FUSED
