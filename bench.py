@@ -286,7 +286,7 @@ def main():
 
     # ---- the other precision modes of the same kernel, same batch (short runs, reported beside the headline)
     others = None
-    if rank == 0 and not args.no_others and P == 1:
+    if rank == 0 and world == 1 and not args.no_others and P == 1:
         from oracle import c_oracle
         others = {}
         nchk = min(F, 256)
@@ -380,7 +380,7 @@ def main():
                              "frac_of_8TBs_spec": achieved / 8000.0,
                              "pair_solves_per_sec": solves / (kernel_ms * 1e-3)},
                 "other_precisions": others, "allgather": gather}
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:      # CPU baseline legs: rank 0 at N=1 only
             cores = os.cpu_count() or 1
             per_core = loop_frames_per_core(C, P, J)
             v, dt = cpu_reference_port(rig, P, J, prm, per_core, cores)
