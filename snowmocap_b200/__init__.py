@@ -17,7 +17,9 @@ __all__ = ["Camera", "CameraGroup"] + sorted(_LAZY)   # `from snowmocap_b200 imp
 
 
 def __getattr__(name):
+    import importlib
     if name in _LAZY:
-        import importlib
         return getattr(importlib.import_module("." + _LAZY[name], __name__), name)
+    if name in ("triangulation", "engine", "dist", "synth"):   # submodules load on first use (they import torch)
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

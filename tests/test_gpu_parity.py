@@ -530,3 +530,65 @@ def test_pack_detections_equals_reference_call_sequence(torch_cuda, P):
         assert nout[f] == n
         if n:
             assert rel_l2(out[f, :n, :, :3], np.array(ref["hrnet_triangulate_points"])) < TOL_FUSED
+
+
+# ---- properties --------------------------------------------------------------------------
+def test_property_score_scaling(torch_cuda):
+    """Scaling every detector score by k > 0 (thresholds that do not gate on the score) scales the keypoint and
+    person scores by k and leaves the 3D points unchanged (weights enter only as ratios)."""
+    torch = torch_cuda
+    rig = floor_rig()
+    d = synth.make_frames(rig, 200, 1, 133, seed=41)
+    prm = dict(synth.DEFAULT_PARAMS, kst=0.0)
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    for precision in ("f64", "mixed"):
+        eng = _engine(rig, prm, precision=precision)
+        a = eng.run(kp, sc, cn, Pout=1)
+        b = eng.run(kp, sc * 4.0, cn, Pout=1)          # power of two: exact in floating point
+        torch.cuda.synchronize()
+        oa, ob = a["out"].cpu().numpy(), b["out"].cpu().numpy()
+        assert np.array_equal(a["nout"].cpu().numpy(), b["nout"].cpu().numpy())
+        np.testing.assert_allclose(ob[..., :3], oa[..., :3], rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(ob[..., 3], 4.0 * oa[..., 3], rtol=1e-6)
+        np.testing.assert_allclose(b["pscores"].cpu().numpy(), 4.0 * a["pscores"].cpu().numpy(), rtol=1e-5)
+
+
+def test_property_frames_are_independent(torch_cuda):
+    """The path has no cross-frame state: any permutation of the frames permutes the outputs (this is what lets
+    frames shard across GPUs), for the single-person and the general kernel."""
+    torch = torch_cuda
+    rng = np.random.default_rng(0)
+    for rig, P, prm, pout in ((floor_rig(), 1, synth.DEFAULT_PARAMS, 1), (synth.ring_rig(5), 3, synth.MULTI_PARAMS, 6)):
+        d = synth.make_frames(rig, 173, P, 33, seed=43, low_score_frac=0.1, drop_prob=0.1)
+        perm = rng.permutation(173)
+        eng = _engine(rig, prm)
+        a = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=pout)
+        b = eng.run(*_to_dev(torch, d["kpts"][perm], d["scores"][perm], d["counts"][perm]), Pout=pout)
+        torch.cuda.synchronize()
+        assert np.array_equal(a["nout"].cpu().numpy()[perm], b["nout"].cpu().numpy())
+        assert np.array_equal(a["out"].cpu().numpy()[perm], b["out"].cpu().numpy())
+        np.testing.assert_allclose(a["pscores"].cpu().numpy()[perm], b["pscores"].cpu().numpy(), rtol=1e-5, atol=1e-7)
+
+
+def test_property_person_order_within_a_camera(torch_cuda):
+    """Detector order inside a camera is arbitrary (main.py:54): permuting it may reorder the emitted persons but
+    the kernel must keep agreeing with the oracle, which follows the reference's list order."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(6)
+    d = synth.make_frames(rig, 60, 3, 17, seed=47, shuffle=False)
+    rng = np.random.default_rng(1)
+    k2, s2 = d["kpts"].copy(), d["scores"].copy()
+    for f in range(60):
+        for c in range(rig.C):
+            p = rng.permutation(3)
+            k2[f, c], s2[f, c] = d["kpts"][f, c][p], d["scores"][f, c][p]
+    prm = synth.MULTI_PARAMS
+    ref = c_oracle.fused(k2, s2, d["counts"], rig.K, rig.R, rig.t, prm, Pout=8)
+    eng = _engine(rig, prm)
+    res = eng.run(*_to_dev(torch, k2, s2, d["counts"]), Pout=8)
+    torch.cuda.synchronize()
+    nout = res["nout"].cpu().numpy()
+    assert np.array_equal(nout, ref["nout"])
+    valid = np.arange(8)[None, :] < np.minimum(nout, 8)[:, None]
+    assert rel_l2(res["out"].cpu().numpy()[valid][..., :3], ref["points"][valid]) < TOL_FUSED
