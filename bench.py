@@ -357,7 +357,10 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_bytes = (12 * C + 16) * P * J * F                     # per output keypoint, per launch
-        kernel_ms = ms / launches                                  # this rank's average launch duration
+        # average duration of the dominant kernel's launch; the streaming general path launches 4 kernels per
+        # step (keep, cluster, fuse, person score), reported as one step
+        per_step = launches / steps
+        kernel_ms = ms / launches if per_step == 1 else ms / steps
         achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
@@ -375,7 +378,9 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
-                             "kernel": {"p1": "snowtri::p1_kernel"}.get(launch_info["kernel"], "snowtri::fused_kernel"),
+                             "kernel": {"p1": "snowtri::p1_kernel",
+                                        "general": "snowtri::gen_keep_kernel + gen_cluster + gen_fuse_kernel + gen_pscore (one step)"
+                                        }.get(launch_info["kernel"], "snowtri::fused_kernel"),
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
                              "frac_of_8TBs_spec": achieved / 8000.0,
                              "pair_solves_per_sec": solves / (kernel_ms * 1e-3)},

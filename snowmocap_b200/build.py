@@ -12,7 +12,7 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsnowtri.so")
 OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = [os.path.join(CSRC, "snowtri_capi.cu"), os.path.join(CSRC, "snowtri_p1.cu"),
-           os.path.join(CSRC, "snowtri_smooth.cu")]
+           os.path.join(CSRC, "snowtri_smooth.cu"), os.path.join(CSRC, "snowtri_general.cu")]
 
 
 def _headers():

@@ -95,6 +95,7 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 6; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->gen_scratch) cudaFree(h->gen_scratch);
     if (h->pipe_in) {
         cudaStreamDestroy(h->pipe_in);
         cudaStreamDestroy(h->pipe_out);
@@ -152,7 +153,7 @@ extern "C" long long snowtri_launch_count(snowtri_t* h) { return h ? h->launches
 
 extern "C" const char* snowtri_last_kernel(snowtri_t* h) {
     if (!h || h->launches == 0) return "";
-    return h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused");
+    return h->last_fly == 3 ? "general" : (h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused"));
 }
 
 extern "C" int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group) {
@@ -357,6 +358,9 @@ extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_sco
 
     if (snowtri_p1_eligible(h, P, Pout))
         return snowtri_p1_run(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+    if (snowtri_general_eligible(h))
+        return snowtri_general_run(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
+    // (fused_kernel: explicit block size requested, or a positive condense_score_tol / kst < 0)
     // The general kernel computes in float32 only on request AND for one person per camera: with several
     // persons, wrongly matched ("ghost") clusters fuse midpoints that lie metres apart, so the float32
     // error of the 1/distance weights (1e-4..1e-3) moves their joints beyond the 1e-4 parity bound.

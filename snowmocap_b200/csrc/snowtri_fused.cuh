@@ -236,6 +236,40 @@ __device__ __forceinline__ float pair_weight_err(const PairSol<float>& s, float 
 constexpr float kDistDelta = 1e-5f;   // metres; bound on the float32 error of a ray-to-ray distance
 constexpr float kGateGuard = 4e-3f;   // relative half-width of the guard band around 1/dthr
 
+// Keep phase (reference triangulation.py:70-79 needs only the SCORE of every joint of every candidate, not the
+// midpoint): with n = hm x hs,  dist = |d.n| / |n|, so
+//     dist > dthr  <=>  (d.n)^2 > dthr^2 * n.n            (no reciprocal, no square root)
+//     score        =   (sm+ss) * 0.0005 * sqrt(n.n) * rsqrt((d.n)^2)    only for the joints that pass the gate
+// 14 FMA-class operations for a gated joint instead of the ~43 of the full pair solve.  Wrongly matched
+// candidates -- the large majority when several persons are in view -- are gated at nearly every joint.
+// `dthr2` = dthr^2, or -1 when dthr < 0 (every finite distance is then "greater").  NaN is not gated (Q8/Q9).
+// float32: `err` accumulates score/dist (see kDistDelta); a gate within its guard band adds the whole score it
+// could contribute.
+template <typename T>
+__device__ __forceinline__ T keep_score(const V3<T>& hm, const V3<T>& hs, const V3<T>& d, T sa, bool low, T dthr2,
+                                        float& err) {
+    V3<T> n;
+    n.x = fma(hm.y, hs.z, -(hm.z * hs.y));
+    n.y = fma(hm.z, hs.x, -(hm.x * hs.z));
+    n.z = fma(hm.x, hs.y, -(hm.y * hs.x));
+    const T nn = dot3(n, n), dn = dot3(n, d), dn2 = dn * dn, lim = dthr2 * nn;
+    if (low) return (T)0;
+    bool gated = dn2 > lim;
+    if constexpr (sizeof(T) == 4) {
+        // gate inside its guard band: either outcome is possible, so the score it could contribute goes into the
+        // error bound (in units of kDistDelta) and the joint is scored as the float32 comparison says
+        if (fabsf(dn2 - lim) < (2.f * kGateGuard) * lim) {
+            const float rdu = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);
+            err += sa * 0.0005f * rdu * (1.0f / kDistDelta);
+        }
+    }
+    if (gated) return (T)0;
+    const T rd = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);  // sqrt(n.n)/|d.n| = 1/dist
+    const T w = sa * (T)0.0005 * rd;
+    if constexpr (sizeof(T) == 4) err = fmaf(w, rd, err);
+    return w;
+}
+
 // Mean candidate score in float64 from the raw inputs in global memory, one warp, lanes over joints
 // (reference triangulation.py:70-79).  Cold path of the float32 kernel's keep decision.
 template <typename T>
@@ -334,7 +368,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
 
     const T inv_dthr = a.inv_dthr;
     const float kst_f = a.prm.kst_f;
-    const float gate_guard = isinf((float)a.inv_dthr) ? 0.f : (float)a.inv_dthr * kGateGuard;
+    const T dthr2 = a.prm.dthr < 0.0 ? (T)-1 : (T)(a.prm.dthr * a.prm.dthr);
     const float2* uv = nullptr;  // current group's (u,v) and scores (smem staging or global)
     const float* sv = nullptr;
 
@@ -479,13 +513,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
                                 V3<T> hs;
                                 float ss;
                                 get_ray(rs + j, sc, hs, ss);
-                                const PairSol<T> s = pair_solve_a(hm[ch], Am[ch], hs, dot3(hs, hs), d);
-                                T w;
-                                if constexpr (sizeof(T) == 4)
-                                    w = pair_weight_err(s, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, inv_dthr, gate_guard, err);
-                                else
-                                    pair_weights(s, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, inv_dthr, w);
-                                sum += w;
+                                sum += keep_score(hm[ch], hs, d, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, dthr2, err);
                             }
                         }
                     } else {
@@ -494,13 +522,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) fused_kernel(const __grid_consta
                             float s0, ss;
                             get_ray(rm + j, mc, h0, s0);
                             get_ray(rs + j, sc, hs, ss);
-                            const PairSol<T> s = pair_solve(h0, hs, d);
-                            T w;
-                            if constexpr (sizeof(T) == 4)
-                                w = pair_weight_err(s, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, inv_dthr, gate_guard, err);
-                            else
-                                pair_weights(s, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, inv_dthr, w);
-                            sum += w;
+                            sum += keep_score(h0, hs, d, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, dthr2, err);
                         }
                     }
                     sum = warp_sum(sum);

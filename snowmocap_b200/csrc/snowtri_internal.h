@@ -35,6 +35,8 @@ struct snowtri_handle {
     cudaStream_t pipe_in, pipe_out;
     cudaEvent_t pipe_ev[SNOWTRI_PIPE_EVENTS], pipe_start;
     int tune_chunk;  // frames per pipeline chunk (0 = automatic)
+    void* gen_scratch;        // candidate scratch of the streaming general path
+    size_t gen_scratch_bytes;
     int allow_f32_multi;  // tests only: float32 general kernel with several persons per camera
     size_t stage_cap[6];
     char err[512];
@@ -57,6 +59,11 @@ static inline int fail(snowtri_t* h, int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                   \
     } while (0)
 
+
+// streaming general path (snowtri_general.cu)
+bool snowtri_general_eligible(const snowtri_t* h);
+int snowtri_general_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int P,
+                        int J, int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream);
 
 // single-person path (snowtri_p1.cu)
 bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout);

@@ -267,7 +267,7 @@ def test_fused_without_counts_and_host_path(torch_cuda):
     res = eng.run_host(d["kpts"], d["scores"], None, Pout=4)
     assert np.array_equal(res["nout"], ref["nout"])
     assert rel_l2(res["out"][..., :3], ref["points"]) < TOL_FUSED
-    assert eng.launch_count == 1
+    assert eng.last_launch_info()["kernel"] == "general" and eng.launch_count == 6   # one chunk: keep, centre, cluster, members, fuse, pscore
 
 
 @pytest.mark.parametrize("chunk", [0, 1, 37, 100000])
