@@ -57,7 +57,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     a.ab = take(fc_max * nc);
 
     const size_t tab = GenTables<T>::bytes(C, a.npairs);
-    const int nch = J <= 32 ? 1 : (J <= 160 ? 5 : 0);
+    const int pb = P <= 4 ? 4 : 8;   // secondary persons scored side by side in the keep kernel
     const int nchunk = (keypoint_num + 31) / 32;
     const size_t R = (size_t)C * P * J;
     int last_grid = 0;
@@ -79,23 +79,22 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
             const bool use_smem = !h->no_fly && staged <= (size_t)h->max_smem;
             const bool small = staged <= (size_t)100 * 1024;   // two or more CTAs per SM
             cudaError_t e = cudaSuccess;
-#define KEEP_LAUNCH(NCH_)                                                                                         \
+#define KEEP_LAUNCH(PB_)                                                                                          \
     do {                                                                                                          \
         if (!use_smem) {                                                                                          \
-            gen_keep_kernel<T, NCH_><<<(unsigned)blocks, kGenWarps * 32, tab, st>>>(a);                           \
+            gen_keep_kernel<T, PB_><<<(unsigned)blocks, kGenWarps * 32, tab, st>>>(a);                           \
         } else if (small) {                                                                                       \
-            e = cudaFuncSetAttribute(gen_keep_smem_kernel<T, NCH_, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            e = cudaFuncSetAttribute(gen_keep_smem_kernel<T, PB_, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)staged);                                                                \
-            gen_keep_smem_kernel<T, NCH_, 256><<<fc, 256, staged, st>>>(a);                                        \
+            gen_keep_smem_kernel<T, PB_, 256><<<fc, 256, staged, st>>>(a);                                        \
         } else {                                                                                                  \
-            e = cudaFuncSetAttribute(gen_keep_smem_kernel<T, NCH_, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+            e = cudaFuncSetAttribute(gen_keep_smem_kernel<T, PB_, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                      (int)staged);                                                                \
-            gen_keep_smem_kernel<T, NCH_, 512><<<fc, 512, staged, st>>>(a);                                        \
+            gen_keep_smem_kernel<T, PB_, 512><<<fc, 512, staged, st>>>(a);                                        \
         }                                                                                                         \
     } while (0)
-            if (nch == 1) KEEP_LAUNCH(1);
-            else if (nch == 5) KEEP_LAUNCH(5);
-            else KEEP_LAUNCH(0);
+            if (pb == 4) KEEP_LAUNCH(4);
+            else KEEP_LAUNCH(8);
 #undef KEEP_LAUNCH
             if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "gen_keep_smem_kernel attribute: %s", cudaGetErrorString(e));
             h->launches += 1;

@@ -99,7 +99,7 @@ __device__ __noinline__ double gen_candidate_mean_f64(const GenArgs& a, const do
 // ---- K1 ------------------------------------------------------------------------------------------------------
 // One (frame, camera pair, main person) item by one warp.  kf/sf point at the frame's (u,v) and scores -- in
 // global memory (gen_keep_kernel) or staged in shared memory (gen_keep_smem_kernel).
-template <typename T, int NCH>  // NCH > 0: main rays of NCH*32 joints held in registers
+template <typename T, int PB>  // PB: secondary persons handled side by side (running sums in registers)
 __device__ __forceinline__ void gen_keep_item(const GenArgs& a, const GenTables<T>& tb, const float2* kf, const float* sf,
                                               int f, int pair, int pm, int lane) {
     const int mc = tb.pairs[pair].x, sc = tb.pairs[pair].y;
@@ -122,71 +122,65 @@ __device__ __forceinline__ void gen_keep_item(const GenArgs& a, const GenTables<
     d.z = (T)(tb.camD[12 * sc + 11] - tb.camD[12 * mc + 11]);
     const T dthr2 = a.prm.dthr < 0.0 ? (T)-1 : (T)(a.prm.dthr * a.prm.dthr);
     const float kst_f = a.prm.kst_f;
-    constexpr int NC = NCH > 0 ? NCH : 1;
-    V3<T> hm[NC];
-    T smT[NC];
-    bool lowm[NC];
-    if (NCH > 0 && !a.all_kept) {
-#pragma unroll
-        for (int ch = 0; ch < NC; ++ch) {
-            const int j = min(ch * 32 + lane, J - 1);
-            const float2 q = kf[rm + j];
-            const float s = sf[rm + j];
-            hm[ch] = back_project<T>(Mm, (T)q.x, (T)q.y);
-            smT[ch] = (T)s;
-            lowm[ch] = s < kst_f;
-        }
+    if (a.all_kept) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
+        for (int ps = lane; ps < P; ps += 32) a.keep[nbase + ps] = ps < cs ? 1 : 0;
+        return;
     }
-    for (int ps = 0; ps < P; ++ps) {
-        if (ps >= cs) {
-            if (lane == 0) a.keep[nbase + ps] = 0;
-            continue;
-        }
-        const int rs = (sc * P + ps) * J;
-        bool kept = true;
-        if (!a.all_kept) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
-            T sum = (T)0;
-            float err = 0.f;
-            if constexpr (NCH > 0) {
+    for (int ps = cs + lane; ps < P; ps += 32) a.keep[nbase + ps] = 0;
+    T Mmr[9];  // both camera matrices in registers
 #pragma unroll
-                for (int ch = 0; ch < NC; ++ch) {
-                    const int j = ch * 32 + lane;
-                    if (j < J) {
-                        const float2 q = kf[rs + j];
-                        const float ss = sf[rs + j];
-                        const V3<T> hs = back_project<T>(Ms, (T)q.x, (T)q.y);
-                        sum += keep_score(hm[ch], hs, d, smT[ch] + (T)ss, lowm[ch] || ss < kst_f, dthr2, err);
-                    }
-                }
-            } else {
-                for (int j = lane; j < J; j += 32) {
-                    const float2 q0 = kf[rm + j], q = kf[rs + j];
-                    const float s0 = sf[rm + j], ss = sf[rs + j];
-                    const V3<T> h0 = back_project<T>(Mm, (T)q0.x, (T)q0.y);
+    for (int i = 0; i < 9; ++i) Mmr[i] = Mm[i];
+    // Joints outer, secondary persons inner: the main ray of a joint is built once and meets PB secondary
+    // persons, each with its own running sum (few registers, so several CTAs stay resident).
+    for (int ps0 = 0; ps0 < cs; ps0 += PB) {
+        T sum[PB];
+        float err[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            sum[u] = (T)0;
+            err[u] = 0.f;
+        }
+        for (int j = lane; j < J; j += 32) {
+            const float2 q0 = kf[rm + j];
+            const float s0 = sf[rm + j];
+            const V3<T> h0 = back_project<T>(Mmr, (T)q0.x, (T)q0.y);
+            const bool low0 = s0 < kst_f;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                if (ps0 + u < cs) {
+                    const int rs = (sc * P + ps0 + u) * J;
+                    const float2 q = kf[rs + j];
+                    const float ss = sf[rs + j];
                     const V3<T> hs = back_project<T>(Ms, (T)q.x, (T)q.y);
-                    sum += keep_score(h0, hs, d, (T)s0 + (T)ss, s0 < kst_f || ss < kst_f, dthr2, err);
+                    sum[u] += keep_score(h0, hs, d, (T)s0 + (T)ss, low0 || ss < kst_f, dthr2, err[u]);
                 }
-            }
-            sum = warp_sum(sum);
-            // mean < ast  <=>  sum < ast*J, decided without the division unless the sum sits on the threshold
-            const double thrJ = a.prm.ast * (double)J, gap = fabs((double)sum - thrJ);
-            kept = !((double)sum < thrJ);  // NaN mean is kept (Q9)
-            if constexpr (sizeof(T) == 4) {
-                // float32 sum closer to the threshold than its own error bound: redo in float64 (discrete decision)
-                err = warp_sum(err);
-                const double slack = (double)kDistDelta * (double)err + 1e-5 * fabs((double)sum);
-                if (!(gap > slack)) kept = !(gen_candidate_mean_f64(a, tb.camD, kf, sf, mc, pm, sc, ps, lane) < a.prm.ast);
-            } else {
-                if (!(gap > 1e-9 * fabs(thrJ))) kept = !((double)sum / (double)J < a.prm.ast);
             }
         }
-        if (lane == 0) a.keep[nbase + ps] = kept ? 1 : 0;
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int ps = ps0 + u;
+            if (ps < cs) {
+                const T tot = warp_sum(sum[u]);
+                // mean < ast  <=>  sum < ast*J, decided without the division unless the sum sits on the threshold
+                const double thrJ = a.prm.ast * (double)J, gap = fabs((double)tot - thrJ);
+                bool kept = !((double)tot < thrJ);  // NaN mean is kept (Q9)
+                if constexpr (sizeof(T) == 4) {
+                    // float32 sum closer to the threshold than its own error bound: redo in float64 (discrete decision)
+                    const float e = warp_sum(err[u]);
+                    const double slack = (double)kDistDelta * (double)e + 1e-5 * fabs((double)tot);
+                    if (!(gap > slack)) kept = !(gen_candidate_mean_f64(a, tb.camD, kf, sf, mc, pm, sc, ps, lane) < a.prm.ast);
+                } else {
+                    if (!(gap > 1e-9 * fabs(thrJ))) kept = !((double)tot / (double)J < a.prm.ast);
+                }
+                if (lane == 0) a.keep[nbase + ps] = kept ? 1 : 0;
+            }
+        }
     }
 }
 
 // Any size: inputs read straight from global memory (L2-resident while the frame is worked on).
-template <typename T, int NCH>
-__global__ void __launch_bounds__(kGenWarps * 32, 2) gen_keep_kernel(const GenArgs a) {
+template <typename T, int PB>
+__global__ void __launch_bounds__(kGenWarps * 32, (sizeof(T) == 8 ? 2 : 3)) gen_keep_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     GenTables<T> tb(smem, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -194,14 +188,14 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) gen_keep_kernel(const GenAr
     if (item >= (long long)a.F * per_frame) return;
     const int f = (int)(item / per_frame), r = (int)(item - (long long)f * per_frame);
     const size_t R = (size_t)a.C * a.P * a.J;
-    gen_keep_item<T, NCH>(a, tb, reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f,
+    gen_keep_item<T, PB>(a, tb, reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f,
                           r / a.P, r % a.P, lane);
 }
 
 // Frames whose raw (u,v,score) fit in shared memory (12 bytes per ray): one CTA per frame stages them once and
 // its warps walk the (pair, main person) items out of shared memory -- each ray is read C-1 times P times.
-template <typename T, int NCH, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) gen_keep_smem_kernel(const GenArgs a) {
+template <typename T, int PB, int NT>
+__global__ void __launch_bounds__(NT, (sizeof(T) == 8 ? 512 : 768) / NT) gen_keep_smem_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     GenTables<T> tb(smem, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -217,11 +211,11 @@ __global__ void __launch_bounds__(NT, 512 / NT) gen_keep_smem_kernel(const GenAr
     }
     __syncthreads();
     const int items = a.npairs * a.P;
-    for (int it = warp; it < items; it += NT / 32) gen_keep_item<T, NCH>(a, tb, uv, sv, f, it / a.P, it % a.P, lane);
+    for (int it = warp; it < items; it += NT / 32) gen_keep_item<T, PB>(a, tb, uv, sv, f, it / a.P, it % a.P, lane);
 }
 
 // ---- K1b: centre-joint midpoint of every kept candidate, float64, one thread per candidate (reference :112,124)
-__global__ void __launch_bounds__(256) gen_centre_kernel(const GenArgs a) {
+__global__ void __launch_bounds__(256) gen_centre_kernel(const __grid_constant__ GenArgs a) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)a.F * a.ncand || !a.keep[n]) return;
     const int f = (int)(n / a.ncand), c = (int)(n - (long long)f * a.ncand);
@@ -248,7 +242,7 @@ __global__ void __launch_bounds__(256) gen_centre_kernel(const GenArgs a) {
 
 // ---- K2 ------------------------------------------------------------------------------------------------------
 // Large candidate counts: one CTA per frame.
-__global__ void __launch_bounds__(256) gen_cluster_block_kernel(const GenArgs a) {
+__global__ void __launch_bounds__(256) gen_cluster_block_kernel(const __grid_constant__ GenArgs a) {
     __shared__ int wtmp[2 * 8 + 4];
     const int f = blockIdx.x;
     const size_t o = (size_t)f * a.ncand;
@@ -258,7 +252,7 @@ __global__ void __launch_bounds__(256) gen_cluster_block_kernel(const GenArgs a)
 }
 
 // Small candidate counts: one warp per frame.
-__global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const GenArgs a) {
+__global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const __grid_constant__ GenArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.x * kGenWarps + warp;
     if (f >= a.F) return;
@@ -283,7 +277,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const 
 // memb2[i] = (main ray row start | pair << 24 ... ) does not fit 32 bits for large rigs, so two words are stored:
 //   .x = row of the main ray      (mc*P + pm)   | mc << 24
 //   .y = row of the secondary ray (sc*P + ps)   | sc << 24        (rows < 2^24, cameras < 2^8)
-__global__ void __launch_bounds__(256) gen_members_kernel(const GenArgs a, uint2* memb2) {
+__global__ void __launch_bounds__(256) gen_members_kernel(const __grid_constant__ GenArgs a, uint2* memb2) {
     const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= (long long)a.F * a.ncand) return;
     const int f = (int)(n / a.ncand), i = (int)(n - (long long)f * a.ncand);
@@ -301,7 +295,7 @@ __global__ void __launch_bounds__(256) gen_members_kernel(const GenArgs a, uint2
 
 // ---- K3 ------------------------------------------------------------------------------------------------------
 template <typename T, typename TD>
-__global__ void __launch_bounds__(kGenWarps * 32) gen_fuse_kernel(const GenArgs a, const uint2* __restrict__ memb2) {
+__global__ void __launch_bounds__(kGenWarps * 32) gen_fuse_kernel(const __grid_constant__ GenArgs a, const uint2* __restrict__ memb2) {
     constexpr bool MIXED = sizeof(TD) != sizeof(T);
     extern __shared__ __align__(16) unsigned char smem[];
     GenTables<T> tb(smem, a);
@@ -401,7 +395,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) gen_fuse_kernel(const GenArgs 
 }
 
 // ---- K4 ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGenWarps * 32) gen_pscore_kernel(const GenArgs a) {
+__global__ void __launch_bounds__(kGenWarps * 32) gen_pscore_kernel(const __grid_constant__ GenArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long row = (long long)blockIdx.x * kGenWarps + warp;
     if (row >= (long long)a.F * a.Pout) return;

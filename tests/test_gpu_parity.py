@@ -592,3 +592,27 @@ def test_property_person_order_within_a_camera(torch_cuda):
     assert np.array_equal(nout, ref["nout"])
     valid = np.arange(8)[None, :] < np.minimum(nout, 8)[:, None]
     assert rel_l2(res["out"].cpu().numpy()[valid][..., :3], ref["points"][valid]) < TOL_FUSED
+
+
+# ---- BASELINE configs[3] and [4] geometry: rigs far beyond what fits in shared memory -------------------------
+@pytest.mark.parametrize("C,P,F,precision", [(16, 8, 3, "f64"), (16, 8, 3, "mixed"), (32, 16, 1, "f64"), (32, 16, 1, "mixed")])
+def test_large_rigs_streaming_path(torch_cuda, C, P, F, precision):
+    """16 cameras x 8 persons and 32 cameras x 16 persons x 133 joints (7 680 / 126 976 candidates per frame):
+    the streaming general path against the C oracle."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(C)
+    d = synth.make_frames(rig, F, P, 133, seed=400 + C, low_score_frac=0.05)
+    prm = synth.MULTI_PARAMS
+    pout = 2 * P
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    eng = _engine(rig, prm, precision=precision)
+    res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=pout)
+    torch.cuda.synchronize()
+    assert eng.last_launch_info()["kernel"] == "general"
+    out, nout = res["out"].cpu().numpy(), res["nout"].cpu().numpy()
+    assert np.array_equal(nout, ref["nout"])
+    valid = np.arange(pout)[None, :] < np.minimum(nout, pout)[:, None]
+    tol = TOL_FUSED if precision == "f64" else TOL_NORTH_STAR / 10
+    assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol
+    assert np.array_equal(out[valid][:, :, 3] == 0, ref["kscores"][valid] == 0)
