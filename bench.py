@@ -32,6 +32,10 @@ WORKLOADS = {
     "cfg2": ("floor", 4, 1, 133, 1 << 17, "default", 1,
              "4 cameras (camera_group_floor.json calibration), 1 person, 133 Wholebody keypoints (BASELINE configs[1])"),
     "cfg3": ("ring", 8, 4, 133, 10000, "multi", 8, "8 cameras, 4 persons, 133 keypoints, 10k frames (BASELINE configs[2])"),
+    "cfg4": ("ring", 16, 8, 133, 2000, "multi", 16,
+             "16 cameras, 8 persons, 133 keypoints (BASELINE configs[3] geometry; 2000 frames per GPU per step)"),
+    "cfg5": ("ring", 32, 16, 133, 200, "multi", 32,
+             "32 cameras, 16 persons, 133 keypoints (BASELINE configs[4] geometry; 200 frames per GPU per step)"),
 }
 
 
@@ -237,7 +241,7 @@ def main():
     parity = None
     if rank == 0:
         from oracle import c_oracle
-        nchk = min(F, 256 if C <= 4 else 32)
+        nchk = min(F, 256 if C <= 4 else (32 if C <= 8 else (4 if C <= 16 else 1)))
         eng.run(kpts, scores, None, Pout=pout, out=out)
         torch.cuda.synchronize()
         ref = c_oracle.fused(kpts[:nchk].cpu().numpy(), scores[:nchk].cpu().numpy(), None, rig.K, rig.R, rig.t, prm, Pout=pout)
