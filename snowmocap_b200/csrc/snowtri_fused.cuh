@@ -270,6 +270,32 @@ __device__ __forceinline__ T keep_score(const V3<T>& hm, const V3<T>& hs, const 
     return w;
 }
 
+// Warp-uniform variant (all 32 lanes must call it; lanes without a joint pass low = true): the reciprocal
+// square roots are behind a vote, so a warp whose 32 joints are all gated -- the normal case for a wrongly
+// matched candidate -- never issues them.
+template <typename T>
+__device__ __forceinline__ void keep_score_warp(const V3<T>& hm, const V3<T>& hs, const V3<T>& d, T sa, bool low,
+                                                T dthr2, T& sum, float& err) {
+    V3<T> n;
+    n.x = fma(hm.y, hs.z, -(hm.z * hs.y));
+    n.y = fma(hm.z, hs.x, -(hm.x * hs.z));
+    n.z = fma(hm.x, hs.y, -(hm.y * hs.x));
+    const T nn = dot3(n, n), dn = dot3(n, d), dn2 = dn * dn, lim = dthr2 * nn;
+    const bool pass = !low && !(dn2 > lim);  // NaN is not gated (Q8/Q9)
+    bool near = false;
+    if constexpr (sizeof(T) == 4) near = !low && fabsf(dn2 - lim) < (2.f * kGateGuard) * lim;
+    if (__any_sync(kFull, pass || near)) {
+        const T rd = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);  // sqrt(n.n)/|d.n| = 1/dist
+        const T w = sa * (T)0.0005 * rd;
+        if (pass) sum += w;
+        if constexpr (sizeof(T) == 4) {
+            // error bound in units of kDistDelta: score/dist, plus the whole score of a joint whose gate could flip
+            if (pass) err = fmaf((float)w, (float)rd, err);
+            if (near) err += (float)w * (1.0f / kDistDelta);
+        }
+    }
+}
+
 // Mean candidate score in float64 from the raw inputs in global memory, one warp, lanes over joints
 // (reference triangulation.py:70-79).  Cold path of the float32 kernel's keep decision.
 template <typename T>

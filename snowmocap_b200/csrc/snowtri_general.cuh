@@ -140,11 +140,13 @@ __device__ __forceinline__ void gen_keep_item(const GenArgs& a, const GenTables<
             sum[u] = (T)0;
             err[u] = 0.f;
         }
-        for (int j = lane; j < J; j += 32) {
+        for (int j0 = 0; j0 < J; j0 += 32) {  // every lane stays in the loop: keep_score_warp votes
+            const bool valid = j0 + lane < J;
+            const int j = valid ? j0 + lane : J - 1;
             const float2 q0 = kf[rm + j];
             const float s0 = sf[rm + j];
             const V3<T> h0 = back_project<T>(Mmr, (T)q0.x, (T)q0.y);
-            const bool low0 = s0 < kst_f;
+            const bool low0 = !valid || s0 < kst_f;
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
                 if (ps0 + u < cs) {
@@ -152,7 +154,7 @@ __device__ __forceinline__ void gen_keep_item(const GenArgs& a, const GenTables<
                     const float2 q = kf[rs + j];
                     const float ss = sf[rs + j];
                     const V3<T> hs = back_project<T>(Ms, (T)q.x, (T)q.y);
-                    sum[u] += keep_score(h0, hs, d, (T)s0 + (T)ss, low0 || ss < kst_f, dthr2, err[u]);
+                    keep_score_warp(h0, hs, d, (T)s0 + (T)ss, low0 || ss < kst_f, dthr2, sum[u], err[u]);
                 }
             }
         }
