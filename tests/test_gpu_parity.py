@@ -616,3 +616,38 @@ def test_large_rigs_streaming_path(torch_cuda, C, P, F, precision):
     tol = TOL_FUSED if precision == "f64" else TOL_NORTH_STAR / 10
     assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol
     assert np.array_equal(out[valid][:, :, 3] == 0, ref["kscores"][valid] == 0)
+
+
+# ---- empty and degenerate inputs ---------------------------------------------------------------------------------
+def test_empty_batch_and_empty_frames(torch_cuda):
+    """F = 0 is a no-op; frames in which no camera sees anybody emit no person (all kernels, all outputs zeroed)."""
+    torch = torch_cuda
+    rig = floor_rig()
+    for P, prm in ((1, synth.DEFAULT_PARAMS), (3, synth.MULTI_PARAMS)):
+        eng = _engine(rig, prm, precision="mixed")
+        z = eng.run(torch.empty((0, 4, P, 17, 2), device="cuda"), torch.empty((0, 4, P, 17), device="cuda"),
+                    torch.empty((0, 4), dtype=torch.int32, device="cuda"), Pout=2)
+        assert z["out"].shape == (0, 2, 17, 4) and z["nout"].shape == (0,)
+        d = synth.make_frames(rig, 40, P, 17, seed=51)
+        counts = d["counts"].copy()
+        counts[::3] = 0                      # every third frame: nobody detected
+        counts[1::3, 1:] = 0                 # every third frame: one camera only -> no pair, no candidate
+        res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], counts), Pout=2)
+        torch.cuda.synchronize()
+        nout, out, ps = res["nout"].cpu().numpy(), res["out"].cpu().numpy(), res["pscores"].cpu().numpy()
+        assert not nout[::3].any() and not nout[1::3].any()
+        assert not out[::3].any() and not out[1::3].any() and not ps[::3].any() and not ps[1::3].any()
+        from oracle import c_oracle
+        ref = c_oracle.fused(d["kpts"], d["scores"], counts, rig.K, rig.R, rig.t, prm, Pout=2)
+        assert np.array_equal(nout, ref["nout"])
+
+
+def test_single_camera_rig_has_no_candidates(torch_cuda):
+    """One camera: no camera pair, so Human_Triangulation yields nothing (reference :56-58 loops are empty)."""
+    torch = torch_cuda
+    rig = synth.ring_rig(4).subset(1)
+    d = synth.make_frames(rig, 5, 2, 17, seed=52)
+    eng = _engine(rig, synth.MULTI_PARAMS)
+    res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=2)
+    torch.cuda.synchronize()
+    assert not res["nout"].cpu().numpy().any() and not res["out"].cpu().numpy().any()
