@@ -198,6 +198,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other precision modes")
+    ap.add_argument("--jit", default="auto", choices=["off", "auto", "always"],
+                    help="rig-specialised single-person kernel compiled at run time (NVRTC)")
     args = ap.parse_args()
     wl = args.workload
     if args.impl == "reference":
@@ -225,6 +227,7 @@ def main():
     if args.precision == "auto":
         args.precision = "f32" if P == 1 else "f64"
     eng = TriangulationEngine(rig.K, rig.R, rig.t, device=local, precision=args.precision, **prm)
+    eng.set_jit(args.jit)
     kpts, scores = synth.make_frames_torch(rig, F, P, J, seed=1234 + rank, device=dev)
     out = {"out": torch.empty((F, pout, J, 4), dtype=torch.float32, device=dev),
            "pscores": torch.empty((F, pout), dtype=torch.float32, device=dev),
@@ -369,7 +372,7 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
-                traffic = json.load(fh).get(f"{wl}_{args.precision}")
+                traffic = json.load(fh).get(f"{wl}_{args.precision}" + ("_jit" if launch_info["kernel"] == "p1-jit" else ""))
         except Exception:
             pass
         solves = C * (C - 1) // 2 * P * P * J * F
@@ -379,10 +382,11 @@ def main():
                 "config": {"workload": wl, "description": desc, "C": C, "P": P, "J": J, "frames_per_gpu": F,
                            "thresholds": prm, "Pout": pout, "timing": "inputs_larger_than_L2" if in_bytes > 126e6 else "inputs_fit_L2",
                            "input_bytes_per_gpu": int(in_bytes), "launch": launch_info},
-                "gpu_launches": int(launches), "clocks": clocks, "parity": parity, "e2e": e2e,
+                "gpu_launches": int(launches), "jit": eng.jit_status, "clocks": clocks, "parity": parity, "e2e": e2e,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": peak_src,
                              "kernel": {"p1": "snowtri::p1_kernel",
+                                        "p1-jit": "p1_jit (snowtri::p1_body specialised for this rig and batch shape with NVRTC)",
                                         "general": "snowtri::gen_keep_kernel + gen_cluster + gen_fuse_kernel + gen_pscore (one step)"
                                         }.get(launch_info["kernel"], "snowtri::fused_kernel"),
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg_bytes),

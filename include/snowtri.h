@@ -92,6 +92,14 @@ int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, c
                      int F, int P, int J, int keypoint_num, int Pout,
                      float* h_out, float* h_pscores, int* h_nout, void* stream);
 
+/* Runtime specialisation of the single-person kernel (float modes) for this handle's camera rig and the batch
+ * shape: the constants are compiled into the instruction stream with NVRTC (about one second, once per rig and
+ * shape; cached in the handle).  mode 0 = never, 1 = automatic (default: batches of >= 65536 frames, or whenever
+ * the kernel is already compiled), 2 = always.  If NVRTC or the driver API cannot be loaded, or compilation
+ * fails, the precompiled kernel runs instead and snowtri_jit_status() says why. */
+int snowtri_set_jit(snowtri_t* h, int mode);
+const char* snowtri_jit_status(snowtri_t* h);
+
 /* Frames per chunk of snowtri_run_host's copy/compute pipeline (0 = automatic, about 24 MB of input). */
 int snowtri_set_pipeline(snowtri_t* h, int frames_per_chunk);
 
@@ -157,7 +165,7 @@ int snowtri_pack_ragged(snowtri_t* h, const float* d_det_kpts, const float* d_de
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */
 int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group);
-const char* snowtri_last_kernel(snowtri_t* h);      /* "p1" (single-person kernel), "fused" or "fused-fly"; "" before any run */
+const char* snowtri_last_kernel(snowtri_t* h);      /* "p1", "p1-jit", "general", "fused" or "fused-fly"; "" before any run */
 int snowtri_version(void);
 
 #ifdef __cplusplus

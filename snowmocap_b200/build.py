@@ -12,7 +12,8 @@ CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libsnowtri.so")
 OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = [os.path.join(CSRC, "snowtri_capi.cu"), os.path.join(CSRC, "snowtri_p1.cu"),
-           os.path.join(CSRC, "snowtri_smooth.cu"), os.path.join(CSRC, "snowtri_general.cu")]
+           os.path.join(CSRC, "snowtri_smooth.cu"), os.path.join(CSRC, "snowtri_general.cu"),
+           os.path.join(CSRC, "snowtri_jit.cu")]
 
 
 def _headers():
@@ -70,5 +71,5 @@ def build(force=False, verbose=False, only=None):
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    subprocess.run([nvcc] + _flags(False) + ["-shared", "-o", LIB] + objs, check=True)
+    subprocess.run([nvcc] + _flags(False) + ["-shared", "-o", LIB] + objs + ["-ldl"], check=True)
     return LIB

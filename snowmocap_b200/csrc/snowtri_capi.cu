@@ -50,6 +50,8 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
     h->device = device;
     h->C = C;
     default_params(&h->prm);
+    h->jit_mode = 1;
+    snprintf(h->jit_status, sizeof(h->jit_status), "not used");
     h->precision = SNOWTRI_PREC_F64;
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
@@ -96,6 +98,7 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     for (int i = 0; i < 6; ++i)
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->gen_scratch) cudaFree(h->gen_scratch);
+    snowtri_jit_free(h);
     if (h->pipe_in) {
         cudaStreamDestroy(h->pipe_in);
         cudaStreamDestroy(h->pipe_out);
@@ -143,6 +146,14 @@ extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ct
     return SNOWTRI_OK;
 }
 
+extern "C" int snowtri_set_jit(snowtri_t* h, int mode) {
+    if (!h || mode < 0 || mode > 2) return fail(h, SNOWTRI_E_ARG, "snowtri_set_jit: mode must be 0 (off), 1 (auto) or 2 (always)");
+    h->jit_mode = mode;
+    return SNOWTRI_OK;
+}
+
+extern "C" const char* snowtri_jit_status(snowtri_t* h) { return h ? h->jit_status : ""; }
+
 extern "C" int snowtri_set_pipeline(snowtri_t* h, int frames_per_chunk) {
     if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_set_pipeline: NULL handle");
     h->tune_chunk = frames_per_chunk > 0 ? frames_per_chunk : 0;
@@ -153,6 +164,7 @@ extern "C" long long snowtri_launch_count(snowtri_t* h) { return h ? h->launches
 
 extern "C" const char* snowtri_last_kernel(snowtri_t* h) {
     if (!h || h->launches == 0) return "";
+    if (h->last_fly == 4) return "p1-jit";
     return h->last_fly == 3 ? "general" : (h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused"));
 }
 

@@ -37,6 +37,9 @@ struct snowtri_handle {
     int tune_chunk;  // frames per pipeline chunk (0 = automatic)
     void* gen_scratch;        // candidate scratch of the streaming general path
     size_t gen_scratch_bytes;
+    int jit_mode;             // 0 off, 1 auto (long batches), 2 always
+    void* jit_cache;          // rig-specialised kernels (snowtri_jit.cu)
+    char jit_status[512];
     int allow_f32_multi;  // tests only: float32 general kernel with several persons per camera
     size_t stage_cap[6];
     char err[512];
@@ -64,6 +67,15 @@ static inline int fail(snowtri_t* h, int code, const char* fmt, ...) {
 bool snowtri_general_eligible(const snowtri_t* h);
 int snowtri_general_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int P,
                         int J, int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream);
+
+// runtime specialisation (snowtri_jit.cu)
+#ifdef __cplusplus
+#include <string>
+bool snowtri_jit_cached(const snowtri_t* h, const std::string& source);
+void* snowtri_jit_get(snowtri_t* h, const std::string& source, const char* name, size_t smem);
+int snowtri_jit_launch(void* fn, int grid, int block, size_t smem, void* stream, void* args);
+void snowtri_jit_free(snowtri_t* h);
+#endif
 
 // single-person path (snowtri_p1.cu)
 bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout);

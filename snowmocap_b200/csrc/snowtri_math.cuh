@@ -13,8 +13,16 @@
 //   score*(W - mid) = (sm+ss)*0.00025*rsqrt(q.q) * v        (what the fuse step accumulates)
 //   dist > dthr  <=>  q.q > (dthr*det)^2
 #pragma once
+#ifdef __CUDACC_RTC__   // runtime compilation (NVRTC) of a rig-specialised kernel: no host headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace snowtri {
 

@@ -2,6 +2,10 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdio.h>
+
+#include <string>
+
 #include "snowtri_internal.h"
 #include "snowtri_p1.cuh"
 
@@ -86,6 +90,44 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
     int grid = h->sm_count * occ;               // one frame range per warp; a short batch uses fewer CTAs
     if ((long long)grid * NW > F) grid = (F + NW - 1) / NW;
     if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+    // Rig-specialised kernel (float modes): constants and batch shape baked in by NVRTC.  Soft failure.
+    if (sizeof(T) == 4 && h->jit_mode > 0 && NT == 256) {
+        char buf[256];
+        std::string src = "#define P1_JIT 1\n";
+        auto def_i = [&](const char* n, int v) { snprintf(buf, sizeof(buf), "#define %s %d\n", n, v); src += buf; };
+        auto def_f = [&](const char* n, float v) {
+            if (isinf(v)) snprintf(buf, sizeof(buf), "#define %s __int_as_float(0x7f800000)\n", n);
+            else snprintf(buf, sizeof(buf), "#define %s %.9ef\n", n, (double)v);
+            src += buf;
+        };
+        def_i("P1_JIT_J", J); def_i("P1_JIT_JOUT", keypoint_num); def_i("P1_JIT_POUT", Pout); def_i("P1_JIT_GW", Gw);
+        def_f("P1_JIT_KST", a.kst_f); def_f("P1_JIT_INV_DTHR", (float)a.inv_dthr); def_f("P1_JIT_GUARD_W", a.guard_w);
+        def_f("P1_JIT_KSCALE_FULL", (float)a.kscale[NP]);
+        auto def_arr = [&](const char* n, const T* v, int cnt) {
+            src += std::string("#define ") + n + " {";
+            for (int i = 0; i < cnt; ++i) { snprintf(buf, sizeof(buf), "%s%.9ef", i ? "," : "", (double)v[i]); src += buf; }
+            src += "}\n";
+        };
+        def_arr("P1_JIT_CAMC", a.camc, C * 12);
+        def_arr("P1_JIT_PDC", a.pdc, NP * 8);
+        snprintf(buf, sizeof(buf),
+                 "#include \"snowtri_p1.cuh\"\nextern \"C\" __global__ void __launch_bounds__(256, %d) p1_jit("
+                 "const __grid_constant__ snowtri::P1Args<float, %d> a) { snowtri::p1_body<float, %s, %d, 256>(a); }\n",
+                 p1_min_blocks<T, TD, C>(), C, sizeof(TD) == 8 ? "double" : "float", C);
+        src += buf;
+        if (h->jit_mode == 2 || F >= 65536 || snowtri_jit_cached(h, src)) {
+            if (void* fn = snowtri_jit_get(h, src, "p1_jit", smem)) {
+                const int rc = snowtri_jit_launch(fn, grid, NT, smem, stream, &a);
+                if (rc == 0) {
+                    h->launches += 1;
+                    h->last_grid = grid; h->last_block = NT; h->last_smem = (int)smem; h->last_G = Gw;
+                    h->last_fly = 4;
+                    return SNOWTRI_OK;
+                }
+                snprintf(h->jit_status, sizeof(h->jit_status), "failed: cuLaunchKernel, CUresult %d", rc);
+            }
+        }
+    }
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel launch failed: %s", cudaGetErrorString(e));

@@ -31,9 +31,9 @@
 // Requirements (checked by the host): P == 1, all_kept (ast <= 0, kst >= 0) and never_filter
 // (score_tol <= 0, kst >= 0); anything else takes fused_kernel.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <math.h>
-
-#include <type_traits>
+#endif
 
 #include "snowtri_math.cuh"
 
@@ -47,11 +47,15 @@ constexpr unsigned kFullMask = 0xffffffffu;
 // pair index of cameras x < y in the reference's (mc, sc) enumeration order
 __host__ __device__ constexpr int pair_index(int C, int x, int y) { return x * C - x * (x + 1) / 2 + y - x - 1; }
 
-// compile-time loop over the camera pairs x < y in the reference's order: f(integral_constant x, y)
+// compile-time loop over the camera pairs x < y in the reference's order: f(IntC<x>, IntC<y>)
+template <int V>
+struct IntC {
+    static constexpr int value = V;
+};
 template <int C, int X = 0, int Y = 1, typename F>
 __device__ __forceinline__ void static_for_pairs(F&& f) {
     if constexpr (X < C - 1) {
-        f(std::integral_constant<int, X>{}, std::integral_constant<int, Y>{});
+        f(IntC<X>{}, IntC<Y>{});
         if constexpr (Y + 1 < C) static_for_pairs<C, X, Y + 1>(f);
         else static_for_pairs<C, X + 1, X + 2>(f);
     }
@@ -133,11 +137,19 @@ __device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2
 #ifndef P1_NI
 #define P1_NI 1   // items a lane solves side by side per step (1 or 2)
 #endif
-// Camera and pair constants come from the kernel-parameter constant bank.  (Baking them into the
-// instruction stream as immediates -- a kernel specialised per rig with NVRTC -- was measured with a
-// statically generated header: 0.535 -> 0.573 of the HBM roof at cfg2; not built this round.)
+// Camera and pair constants come from the kernel-parameter constant bank in the precompiled kernels.
+#ifdef P1_JIT
+// Rig-specialised build (NVRTC, see snowtri_jit.cu): the generated translation unit defines P1_JIT_CAMC / _PDC
+// (brace lists of the camera and pair constants) and the scalar P1_JIT_* values before including this header, so
+// they reach the instruction stream as immediates and the index arithmetic on J, Jout, Pout folds.
+__device__ constexpr float kJ_camc[] = P1_JIT_CAMC;
+__device__ constexpr float kJ_pdc[] = P1_JIT_PDC;
+#define P1_CAMC(T, i) ((T)kJ_camc[i])
+#define P1_PDC(T, i) ((T)kJ_pdc[i])
+#else
 #define P1_CAMC(T, i) (a.camc[i])
 #define P1_PDC(T, i) (a.pdc[i])
+#endif
 // resident CTAs per SM the register allocation is held to (256-thread CTAs)
 template <typename T, typename TD, int C>
 constexpr int p1_min_blocks() {
@@ -149,7 +161,7 @@ constexpr int p1_min_blocks() {
 }
 
 template <typename T, typename TD, int C, int NT>
-__global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(const __grid_constant__ P1Args<T, C> a) {
+__device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
     constexpr int NP = C * (C - 1) / 2;
     constexpr int NW = NT / 32;
     constexpr unsigned ALL = (NP >= 32) ? 0xffffffffu : ((1u << NP) - 1u);
@@ -157,7 +169,15 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
     constexpr int NI = P1_NI;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef P1_JIT
+    constexpr int J = P1_JIT_J, Jout = P1_JIT_JOUT, Pout = P1_JIT_POUT, Gw = P1_JIT_GW;
+    constexpr float kst_f = P1_JIT_KST, guard_w = P1_JIT_GUARD_W;
+    constexpr T inv_dthr = (T)P1_JIT_INV_DTHR, kscale_full = (T)P1_JIT_KSCALE_FULL;
+#else
     const int J = a.J, Jout = a.Jout, Pout = a.Pout, Gw = a.Gw;
+    const float kst_f = a.kst_f, guard_w = a.guard_w;
+    const T inv_dthr = a.inv_dthr, kscale_full = a.kscale[NP];
+#endif
     // per-warp scratch: centres (Gw*NP*3 doubles), person-score columns (Gw*32 floats), cluster masks (Gw*Pout words)
     const int warp_bytes = Gw * NP * 24 + Gw * 128 + ((Gw * Pout * 4 + 7) & ~7);
     double* cen = reinterpret_cast<double*>(smem + (size_t)warp * warp_bytes);
@@ -338,7 +358,7 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
                     A[u][c] = dot3(h[u][c], h[u][c]);
                     // a score below the keypoint threshold kills every pair of its camera: poison it so that
                     // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
-                    sc[u][c] = s1n[u][c] < a.kst_f ? (T)-1e30 : (T)s1n[u][c];
+                    sc[u][c] = s1n[u][c] < kst_f ? (T)-1e30 : (T)s1n[u][c];
                 }
             }
             // next items of this lane: issue their loads now, use them one step later
@@ -400,9 +420,9 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
                 }
                 const T r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
                 const T rd = r * s.det;                   // 1/dist
-                if constexpr (sizeof(T) == 4) margin[u] = fminf(margin[u], fabsf(rd - a.inv_dthr));
+                if constexpr (sizeof(T) == 4) margin[u] = fminf(margin[u], fabsf(rd - inv_dthr));
                 T gq = fmax(sc[u][x] + sc[u][y], (T)0) * r;
-                if (rd < a.inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
+                if (rd < inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
                 const T w = gq * s.det;
                 S[u] += w;
                 al[u][x] = fma(gq, s.n0, al[u][x]);
@@ -413,21 +433,21 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
             };
             if (full) {
                 static_for_pairs<C>([&](auto xc, auto yc) {
-                    pair(xc, yc, std::integral_constant<int, 0>{});
-                    if constexpr (NI > 1) pair(xc, yc, std::integral_constant<int, NI - 1>{});
+                    pair(xc, yc, IntC<0>{});
+                    if constexpr (NI > 1) pair(xc, yc, IntC<NI - 1>{});
                 });
             } else {
                 static_for_pairs<C>([&](auto xc, auto yc) {
                     constexpr int e = pair_index(C, decltype(xc)::value, decltype(yc)::value);
-                    if ((mask[0] >> e) & 1u) pair(xc, yc, std::integral_constant<int, 0>{});
+                    if ((mask[0] >> e) & 1u) pair(xc, yc, IntC<0>{});
                     if constexpr (NI > 1)
-                        if ((mask[NI - 1] >> e) & 1u) pair(xc, yc, std::integral_constant<int, NI - 1>{});
+                        if ((mask[NI - 1] >> e) & 1u) pair(xc, yc, IntC<NI - 1>{});
                 });
             }
 #pragma unroll
             for (int u = 0; u < NI; ++u) {
                 float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (sizeof(T) == 4 && margin[u] < a.guard_w && mask[u]) {
+                if (sizeof(T) == 4 && margin[u] < guard_w && mask[u]) {
                     // a float32 distance within the guard band of dthr: decide in float64
                     o = p1_item_exact<T, TD, C>(a, kpt + off[u], sct + off[u], mask[u]);
                 } else if (S[u] != (T)0) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
@@ -442,7 +462,7 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
                     o.x = (float)(fma((T)0.5, X, Xm[u]) * rS);
                     o.y = (float)(fma((T)0.5, Y, Ym[u]) * rS);
                     o.z = (float)(fma((T)0.5, Z, Zm[u]) * rS);
-                    o.w = (float)(S[u] * (full ? a.kscale[NP] : a.kscale[__popc(mask[u])]));
+                    o.w = (float)(S[u] * (full ? kscale_full : a.kscale[__popc(mask[u])]));
                 }
                 if (live[u]) {
                     outt[(g[u] * Pout) * Jout + j[u]] = o;
@@ -489,6 +509,11 @@ __global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(con
         }
         __syncwarp();
     }
+}
+
+template <typename T, typename TD, int C, int NT>
+__global__ void __launch_bounds__(NT, (p1_min_blocks<T, TD, C>())) p1_kernel(const __grid_constant__ P1Args<T, C> a) {
+    p1_body<T, TD, C, NT>(a);
 }
 
 }  // namespace snowtri

@@ -77,6 +77,14 @@ class TriangulationEngine:
     def set_tuning(self, frames_per_group=0, max_ctas=0, threads=0):
         _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas), int(threads)), self._h)
 
+    def set_jit(self, mode="auto"):
+        """Rig-specialised single-person kernel compiled at run time with NVRTC: "off", "auto" (long batches) or "always"."""
+        _lib.check(self._lib.snowtri_set_jit(self._h, {"off": 0, "auto": 1, "always": 2}[mode]), self._h)
+
+    @property
+    def jit_status(self):
+        return (self._lib.snowtri_jit_status(self._h) or b"").decode()
+
     def set_pipeline(self, frames_per_chunk=0):
         """Frames per chunk of run_host's copy/compute pipeline (0 = automatic)."""
         _lib.check(self._lib.snowtri_set_pipeline(self._h, int(frames_per_chunk)), self._h)

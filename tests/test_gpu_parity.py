@@ -651,3 +651,45 @@ def test_single_camera_rig_has_no_candidates(torch_cuda):
     res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=2)
     torch.cuda.synchronize()
     assert not res["nout"].cpu().numpy().any() and not res["out"].cpu().numpy().any()
+
+
+# ---- rig-specialised single-person kernel (NVRTC) ----------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["f32", "mixed"])
+@pytest.mark.parametrize("case", [0, 2, 3, 7])
+def test_jit_specialised_kernel_matches_precompiled(torch_cuda, precision, case):
+    """snowtri_set_jit(always): the kernel compiled at run time for this rig and batch shape must reproduce the
+    precompiled kernel (same source, constants as immediates) and the oracle; a second run hits the cache."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rname, F, J, prm, pout, knum, kw = P1_CASES[case]
+    rig = _rig(rname)
+    d = synth.make_frames(rig, F, 1, J, seed=600 + case, **kw)
+    jout = knum or J
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    eng = _engine(rig, prm, precision=precision)
+    eng.set_jit("off")
+    base = eng.run(kp, sc, cn, Pout=pout, keypoint_num=jout)
+    torch.cuda.synchronize()
+    assert eng.last_launch_info()["kernel"] == "p1"
+    base = {k: v.clone() for k, v in base.items()}
+    eng.set_jit("always")
+    for rep in range(2):
+        res = eng.run(kp, sc, cn, Pout=pout, keypoint_num=jout)
+        torch.cuda.synchronize()
+        assert eng.last_launch_info()["kernel"] == "p1-jit", eng.jit_status
+        assert eng.jit_status.startswith("compiled")
+        assert torch.equal(res["nout"], base["nout"])
+        np.testing.assert_allclose(res["out"].cpu().numpy(), base["out"].cpu().numpy(), rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(res["pscores"].cpu().numpy(), base["pscores"].cpu().numpy(), rtol=2e-5, atol=1e-6)
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout, keypoint_num=jout)
+    nout = res["nout"].cpu().numpy()
+    assert np.array_equal(nout, ref["nout"])
+    valid = np.arange(pout)[None, :] < np.minimum(nout, pout)[:, None]
+    if valid.any():
+        assert rel_l2(res["out"].cpu().numpy()[valid][:, :, :3], ref["points"][valid]) < TOL_NORTH_STAR / 10
+    eng.set_params(dthr=0.04)      # a threshold is baked in too: changing it must compile a new kernel, not reuse
+    res2 = eng.run(kp, sc, cn, Pout=pout, keypoint_num=jout)
+    torch.cuda.synchronize()
+    ref2 = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, dict(prm, dthr=0.04), Pout=pout,
+                          keypoint_num=jout)
+    assert np.array_equal(res2["out"].cpu().numpy()[..., 3] == 0, np.where(np.arange(pout)[None, :, None] < np.minimum(ref2["nout"], pout)[:, None, None], ref2["kscores"] == 0, True))
