@@ -3,6 +3,7 @@
 #include <string.h>
 
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -113,7 +114,8 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
         snprintf(buf, sizeof(buf),
                  "#include \"snowtri_p1.cuh\"\nextern \"C\" __global__ void __launch_bounds__(256, %d) p1_jit("
                  "const __grid_constant__ snowtri::P1Args<float, %d> a) { snowtri::p1_body<float, %s, %d, 256>(a); }\n",
-                 p1_min_blocks<T, TD, C>(), C, sizeof(TD) == 8 ? "double" : "float", C);
+                 getenv("SNOWTRI_JIT_MINB") ? atoi(getenv("SNOWTRI_JIT_MINB")) : p1_min_blocks<T, TD, C>(), C,
+                 sizeof(TD) == 8 ? "double" : "float", C);
         src += buf;
         if (h->jit_mode == 2 || F >= 65536 || snowtri_jit_cached(h, src)) {
             if (void* fn = snowtri_jit_get(h, src, "p1_jit", smem)) {

@@ -18,7 +18,7 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $out/bench_r
 timeout 300 ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_cfg2.csv \
     python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e --no-others > $out/ncu_launches.log 2>&1
 for prec in f32 mixed f64; do
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:p1_kernel -s 4 -c 1 -f -o $out/p1_cfg2_$prec \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:p1_ -s 4 -c 1 -f -o $out/p1_cfg2_$prec \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-others --precision $prec > $out/ncu_full_cfg2_$prec.log 2>&1
 done
 for k in gen_keep gen_fuse; do
