@@ -95,6 +95,21 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
     if (sizeof(T) == 4 && h->jit_mode > 0 && NT == 256) {
         char buf[256];
         std::string src = "#define P1_JIT 1\n";
+        // with the constants out of the register file, two items per lane per step pay off in all-float32
+        // (measured at cfg2: 0.608 -> 0.640 of the HBM roof; in mixed mode the float64 rays make it spill)
+        if (sizeof(TD) == 4 && C <= 4) src += "#define P1_NI 2\n";
+        if (const char* extra = getenv("SNOWTRI_JIT_DEFINES")) {  // experiments: "P1_NI=2 P1_L2_AHEAD=1"
+            std::string e(extra);
+            size_t pos = 0;
+            while (pos < e.size()) {
+                size_t sp = e.find(' ', pos);
+                if (sp == std::string::npos) sp = e.size();
+                std::string tok = e.substr(pos, sp - pos);
+                const size_t eq = tok.find('=');
+                if (!tok.empty()) src += "#define " + (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) + "\n";
+                pos = sp + 1;
+            }
+        }
         auto def_i = [&](const char* n, int v) { snprintf(buf, sizeof(buf), "#define %s %d\n", n, v); src += buf; };
         auto def_f = [&](const char* n, float v) {
             if (isinf(v)) snprintf(buf, sizeof(buf), "#define %s __int_as_float(0x7f800000)\n", n);

@@ -134,6 +134,9 @@ __device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2
 #ifndef P1_KEEP
 #define P1_KEEP 1
 #endif
+#ifndef P1_L2_AHEAD
+#define P1_L2_AHEAD 0   // per-lane L2 prefetch this many steps beyond the register prefetch (0 = off)
+#endif
 #ifndef P1_NI
 #define P1_NI 1   // items a lane solves side by side per step (1 or 2)
 #endif
@@ -385,6 +388,23 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                     }
                 }
             }
+#if P1_L2_AHEAD
+            // the items P1_L2_AHEAD steps further: pull their lines into L2 so that the register loads above
+            // (one step ahead) see L2 latency, not HBM latency
+            if (q0 + 32 * NI * (1 + P1_L2_AHEAD) < nitems) {
+                int gp = gn[NI - 1], jp = jn[NI - 1];
+#pragma unroll
+                for (int k = 0; k < NI * P1_L2_AHEAD; ++k) advance(gp, jp);
+                if (gp < Gc) {
+                    const int offp = gp * CJ + jp;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(kpc[c] + offp));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(scc[c] + offp));
+                    }
+                }
+            }
+#endif
 
             // output slot 0: the unrolled path
             unsigned mask[NI];

@@ -693,3 +693,22 @@ def test_jit_specialised_kernel_matches_precompiled(torch_cuda, precision, case)
     ref2 = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, dict(prm, dthr=0.04), Pout=pout,
                           keypoint_num=jout)
     assert np.array_equal(res2["out"].cpu().numpy()[..., 3] == 0, np.where(np.arange(pout)[None, :, None] < np.minimum(ref2["nout"], pout)[:, None, None], ref2["kscores"] == 0, True))
+
+
+def test_jit_failure_falls_back_to_precompiled_kernel(torch_cuda, monkeypatch):
+    """A runtime-compilation failure is soft: the precompiled kernel runs, the result is unchanged and the reason is
+    reported.  (The failure is provoked with an experiment hook that injects a macro into the generated source.)"""
+    torch = torch_cuda
+    rig = floor_rig()
+    d = synth.make_frames(rig, 50, 1, 133, seed=61)
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    eng = _engine(rig, synth.DEFAULT_PARAMS, precision="f32")
+    eng.set_jit("off")
+    base = eng.run(kp, sc, cn, Pout=1)["out"].clone()
+    monkeypatch.setenv("SNOWTRI_JIT_DEFINES", "P1_NI=not_a_number")
+    eng.set_jit("always")
+    res = eng.run(kp, sc, cn, Pout=1)
+    torch.cuda.synchronize()
+    assert eng.last_launch_info()["kernel"] == "p1"
+    assert eng.jit_status.startswith("failed: nvrtc"), eng.jit_status
+    assert torch.equal(res["out"], base)
