@@ -58,7 +58,7 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
         }
     auto kern = p1_kernel<T, TD, C, NT>;
     int occ = 0;
-    auto smem_of = [&](int gw) -> size_t { return (size_t)NW * ((size_t)gw * NP * 24 + (size_t)gw * 128 + (((size_t)gw * Pout * 4 + 7) & ~(size_t)7)); };
+    auto smem_of = [&](int gw) -> size_t { return (size_t)NW * ((size_t)gw * NP * 24 + (((size_t)gw * 33 * 4 + 7) & ~(size_t)7) + (((size_t)gw * Pout * 4 + 7) & ~(size_t)7)); };
     // frames per warp tile: few wasted lanes in the last 32-item step, enough tiles to fill every warp slot
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8) > 49152 ? (int)smem_of(8) : 49152) != cudaSuccess)
         cudaGetLastError();

@@ -17,8 +17,8 @@
 //   * sum(score * point) is accumulated as  sum(w*mid) + 1/2 * sum_c alpha_c * h_c  with one scalar
 //     alpha per camera instead of a 3-vector per pair (see snowtri_math.cuh for the algebra);
 //   * the person score (mean keypoint score, reference :150) is accumulated in registers per lane,
-//     parked in a per-warp shared-memory column when the lane crosses a frame boundary and reduced
-//     with a fixed-order warp shuffle: deterministic, no re-read of the output.
+//     parked in a per-warp shared-memory column when the lane crosses a frame boundary and added up in a
+//     fixed order by one lane per frame: deterministic, no atomics, no re-read of the output.
 //
 // Precision (template T = bulk arithmetic, TD = arithmetic of the ray-distance numerator d.(hm x hs)):
 //   <double,double>  everything in float64, like the reference.
@@ -182,10 +182,10 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
     const T inv_dthr = a.inv_dthr, kscale_full = a.kscale[NP];
 #endif
     // per-warp scratch: centres (Gw*NP*3 doubles), person-score columns (Gw*32 floats), cluster masks (Gw*Pout words)
-    const int warp_bytes = Gw * NP * 24 + Gw * 128 + ((Gw * Pout * 4 + 7) & ~7);
+    const int warp_bytes = Gw * NP * 24 + ((Gw * 33 * 4 + 7) & ~7) + ((Gw * Pout * 4 + 7) & ~7);
     double* cen = reinterpret_cast<double*>(smem + (size_t)warp * warp_bytes);
     float* part = reinterpret_cast<float*>(cen + Gw * NP * 3);
-    uint32_t* meta = reinterpret_cast<uint32_t*>(part + Gw * 32);
+    uint32_t* meta = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(part) + ((Gw * 33 * 4 + 7) & ~7));
 
     const float2* kp2 = reinterpret_cast<const float2*>(a.kpts);
     const int CJ = C * J;
@@ -285,7 +285,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
             cen[3 * idx + 1] = w.y;
             cen[3 * idx + 2] = w.z;
         }
-        for (int gg = 0; gg < Gc; ++gg) part[gg * 32 + lane] = 0.f;
+        for (int gg = 0; gg < Gc; ++gg) part[gg * 33 + lane] = 0.f;
         __syncwarp();
 
         // ---- greedy clustering on pair bit masks, one lane per frame (reference :107-134) ----------
@@ -487,7 +487,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                 if (live[u]) {
                     outt[(g[u] * Pout) * Jout + j[u]] = o;
                     if (g[u] != gacc) {
-                        part[gacc * 32 + lane] = acc;
+                        part[gacc * 33 + lane] = acc;
                         acc = 0.f;
                         gacc = g[u];
                     }
@@ -506,13 +506,22 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                 j[u] = jn[u];
             }
         }
-        if (lane < nitems) part[gacc * 32 + lane] = acc;
+        if (lane < nitems) part[gacc * 33 + lane] = acc;
         __syncwarp();
 
         // ---- person score = mean keypoint score (reference :150) ----------------------------------------
-        for (int gg = 0; gg < Gc; ++gg) {
-            const float s = warp_sum(part[gg * 32 + lane]);
-            if (lane == 0) a.pscores[(size_t)(f0 + gg) * Pout] = s / (float)Jout;
+        // lane gg adds up the 32 columns of frame gg (row stride 33: conflict-free), four running sums
+        if (lane < Gc) {
+            const float* row = part + lane * 33;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                s0 += row[i];
+                s1 += row[i + 1];
+                s2 += row[i + 2];
+                s3 += row[i + 3];
+            }
+            a.pscores[(size_t)(f0 + lane) * Pout] = ((s0 + s1) + (s2 + s3)) / (float)Jout;
         }
         if (!multi) {
             for (int row = lane; row < Gc * Pout; row += 32)
