@@ -37,6 +37,8 @@ struct snowtri_handle {
     int tune_chunk;  // frames per pipeline chunk (0 = automatic)
     void* gen_scratch;        // candidate scratch of the streaming general path
     size_t gen_scratch_bytes;
+    void* p1_args;            // host copy of the single-person kernel's argument block
+    size_t p1_args_bytes;
     int jit_mode;             // 0 off, 1 auto (long batches), 2 always
     void* jit_cache;          // rig-specialised kernels (snowtri_jit.cu)
     char jit_status[512];

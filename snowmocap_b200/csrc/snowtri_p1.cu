@@ -22,7 +22,14 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
 #else
     constexpr int NT = 256, NW = NT / 32;
 #endif
-    static P1Args<T, C> a;  // > 1 KB: keep it off the stack; a handle is not thread-safe anyway
+    // the argument block is a few KB: it lives in the handle (one handle per thread by contract), not in a static
+    if (h->p1_args_bytes < sizeof(P1Args<T, C>)) {
+        free(h->p1_args);
+        h->p1_args = aligned_alloc(64, (sizeof(P1Args<T, C>) + 63) & ~(size_t)63);  // the block has 32-byte aligned members
+        h->p1_args_bytes = h->p1_args ? sizeof(P1Args<T, C>) : 0;
+        if (!h->p1_args) return fail(h, SNOWTRI_E_NOMEM, "snowtri_run: out of host memory");
+    }
+    P1Args<T, C>& a = *reinterpret_cast<P1Args<T, C>*>(h->p1_args);
     memset(&a, 0, sizeof(a));
     a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
     a.out = d_out; a.pscores = d_pscores; a.nout = d_nout;

@@ -42,6 +42,7 @@ struct snowtri_smooth_state {
     size_t work_chunks;
     double apow_T;
     int sequential;   // 1 = always the single-launch sequential kernel
+    double apow_host[(128 + 1) * 9];  // (kChunk + 1) matrices
 };
 
 namespace snowtri {
@@ -483,7 +484,7 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
         if (!s->d_apow) CUDA_TRY(h, cudaMalloc(&s->d_apow, (size_t)(kChunk + 1) * 9 * sizeof(double)));
         const double T = delta_time, g = T / k2;
         const double A[9] = {0, 0, 0, 0, 1, T, -a.k3 / k2, -g, 1 - g * (T + a.k1)};
-        static double pw[(kChunk + 1) * 9];
+        double* pw = s->apow_host;
         const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
         memcpy(pw, I, sizeof(I));
         for (int n = 1; n <= kChunk; ++n)
@@ -493,8 +494,8 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
                     for (int m_ = 0; m_ < 3; ++m_) v += A[r_ * 3 + m_] * pw[(n - 1) * 9 + m_ * 3 + c_];
                     pw[n * 9 + r_ * 3 + c_] = v;
                 }
-        CUDA_TRY(h, cudaMemcpyAsync(s->d_apow, pw, sizeof(pw), cudaMemcpyHostToDevice, st));
-        CUDA_TRY(h, cudaStreamSynchronize(st));  // pw is a host static: do not let a later call overwrite it in flight
+        CUDA_TRY(h, cudaMemcpyAsync(s->d_apow, pw, sizeof(s->apow_host), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(h, cudaStreamSynchronize(st));  // pageable source: make sure the copy has read it before it can change
         s->apow_T = delta_time;
     }
     ChunkArgs ca;
