@@ -161,6 +161,15 @@ int snowtri_pack_ragged(snowtri_t* h, const float* d_det_kpts, const float* d_de
                         const long long* d_offsets, int F, int P, int J,
                         float* d_kpts, float* d_scores, int* d_counts, void* stream);
 
+/* Optional DLT mode (NOT what the reference computes): one person per camera,
+ * every (frame, joint) is triangulated from all cameras whose score passes keypoint_score_threshold by the
+ * homogeneous linear method -- rows xn*Q[2]-Q[0], yn*Q[2]-Q[1] with Q = [R^T | -R^T t] and (xn,yn) = K^-1 [u v 1],
+ * solution = eigenvector of the 4x4 normal matrix with the smallest eigenvalue.
+ *   d_kpts (F,C,1,J,2), d_scores (F,C,1,J) float32;  d_out (F,J,4) float32: x, y, z, number of views used
+ *   (fewer than two views: zeros).  accumulate_f64 = 1 builds the normal matrix in float64 instead of float32. */
+int snowtri_dlt_run(snowtri_t* h, const float* d_kpts, const float* d_scores, int F, int J, float* d_out,
+                    int accumulate_f64, void* stream);
+
 /* Introspection. */
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */

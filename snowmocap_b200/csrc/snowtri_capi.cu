@@ -67,8 +67,11 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     double* cam = (double*)malloc(sizeof(double) * 12 * C);
+    h->kinv_host = (double*)malloc(sizeof(double) * 9 * C);
+    h->r_host = (double*)malloc(sizeof(double) * 9 * C);
+    memcpy(h->r_host, R, sizeof(double) * 9 * C);
     for (int c = 0; c < C; ++c) {
-        double Kinv[9];
+        double* Kinv = h->kinv_host + 9 * c;
         inv3(K + 9 * c, Kinv);
         for (int r = 0; r < 3; ++r)
             for (int k = 0; k < 3; ++k) {
@@ -84,6 +87,8 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
     if (e != cudaSuccess) {
         if (h->d_cam) cudaFree(h->d_cam);
         free(cam);
+        free(h->kinv_host);
+        free(h->r_host);
         free(h);
         return fail(nullptr, SNOWTRI_E_CUDA, "snowtri_create: %s", cudaGetErrorString(e));
     }
@@ -108,6 +113,8 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     }
     if (h->d_cam) cudaFree(h->d_cam);
     free(h->cam_host);
+    free(h->kinv_host);
+    free(h->r_host);
     free(h);
     return SNOWTRI_OK;
 }

@@ -23,6 +23,8 @@ struct snowtri_handle {
     int device, C, sm_count, max_smem;
     double* d_cam;  // (C,12) M = R*inv(K), t
     double* cam_host;
+    double* kinv_host;  // (C,9) inverse intrinsics and (C,9) camera->world rotations, kept for the DLT mode
+    double* r_host;
     int smem_per_sm;
     snowtri::Params prm;
     int precision;

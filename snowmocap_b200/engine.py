@@ -142,6 +142,19 @@ class TriangulationEngine:
                        self._h)
         return out
 
+    # -- optional DLT mode (not the reference's estimator) ---------------------------------------
+    def dlt(self, kpts, scores, accumulate_f64=False):
+        """Homogeneous linear triangulation of every (frame, joint) from all cameras with score >= kst; one person
+        per camera: kpts (F,C,1,J,2), scores (F,C,1,J).  Returns (F,J,4) float32: x, y, z, views used."""
+        F, C, P, J = self._check_inputs(kpts, scores, None)
+        if P != 1:
+            raise ValueError("the DLT mode takes one (already matched) person per camera")
+        out = torch.empty((F, J, 4), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.snowtri_dlt_run(self._h, _ptr(kpts), _ptr(scores), F, J, _ptr(out),
+                                                 1 if accumulate_f64 else 0, _stream()), self._h)
+        return out
+
     # -- ragged ingestion -----------------------------------------------------------------
     def pack_detections(self, detections, P=None):
         """Detector outputs of a clip -> dense device batch.  ``detections[f][c]`` is the pair

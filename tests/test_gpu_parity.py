@@ -712,3 +712,24 @@ def test_jit_failure_falls_back_to_precompiled_kernel(torch_cuda, monkeypatch):
     assert eng.last_launch_info()["kernel"] == "p1"
     assert eng.jit_status.startswith("failed: nvrtc"), eng.jit_status
     assert torch.equal(res["out"], base)
+
+
+# ---- optional DLT mode ------------------------------------------------------------------------
+@pytest.mark.parametrize("rname,f64acc,tol", [("floor4", False, 2e-5), ("floor4", True, 1e-6), ("ring8", False, 2e-5),
+                                                ("ring2", True, 1e-6)])
+def test_dlt_mode_matches_numpy_svd(torch_cuda, rname, f64acc, tol):
+    """Homogeneous linear triangulation against np.linalg.svd of the same 2V x 4 system (not a reference parity
+    test: snowvision has no DLT).  Also recovers the synthetic ground truth to the noise level."""
+    torch = torch_cuda
+    from oracle import dlt_oracle
+    rig = _rig(rname)
+    d = synth.make_frames(rig, 40, 1, 133, seed=71, low_score_frac=0.15, shuffle=False)
+    ref = dlt_oracle.dlt_points(d["kpts"], d["scores"], rig.K, rig.R, rig.t, kst=0.5)
+    eng = _engine(rig, synth.DEFAULT_PARAMS)
+    out = eng.dlt(*_to_dev(torch, d["kpts"], d["scores"]), accumulate_f64=f64acc).cpu().numpy()
+    assert np.array_equal(out[..., 3], ref[..., 3])
+    m = ref[..., 3] >= 2
+    assert not out[~m][..., :3].any()
+    assert rel_l2(out[m][..., :3], ref[m][..., :3]) < tol
+    full = ref[..., 3] == rig.C
+    assert np.abs(ref[full][..., :3] - d["truth"][:, 0][full]).max() < 0.05     # 0.5 px noise at ~5 m: centimetres
