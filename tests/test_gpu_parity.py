@@ -733,3 +733,45 @@ def test_dlt_mode_matches_numpy_svd(torch_cuda, rname, f64acc, tol):
     assert rel_l2(out[m][..., :3], ref[m][..., :3]) < tol
     full = ref[..., 3] == rig.C
     assert np.abs(ref[full][..., :3] - d["truth"][:, 0][full]).max() < 0.05     # 0.5 px noise at ~5 m: centimetres
+
+
+# ---- randomized differential test: random rigs, shapes and thresholds against the C oracle ---------------------
+@pytest.mark.parametrize("seed", range(60))
+def test_random_configurations_vs_c_oracle(torch_cuda, seed):
+    """Random camera count, persons, joints, ragged counts and thresholds (including the reference's defaults,
+    zero / tiny / huge tolerances, num_tol above the cluster sizes, truncated keypoint_num).  float64 must match the
+    oracle to storage precision; the float modes must emit the same persons and hold the north_star bound."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rng = np.random.default_rng(1000 + seed)
+    C = int(rng.integers(2, 9))
+    P = int(rng.choice([1, 1, 2, 3]))
+    J = int(rng.choice([1, 5, 17, 33, 64, 133]))
+    F = int(rng.integers(1, 70))
+    rig = synth.ring_rig(C, seed=seed)
+    d = synth.make_frames(rig, F, P, J, seed=2000 + seed, low_score_frac=float(rng.choice([0.0, 0.1, 0.5])),
+                          drop_prob=float(rng.choice([0.0, 0.2, 0.6])), noise_px=float(rng.choice([0.3, 1.0, 3.0])))
+    prm = dict(kst=float(rng.choice([0.0, 0.5, 0.7])), ast=float(rng.choice([0.0, 0.0, 0.05, 0.3])),
+               dthr=float(rng.choice([0.05, 0.01, 0.5])), cond_tol=float(rng.choice([0.1, 0.3, 10.0, 0.005])),
+               num_tol=int(rng.choice([0, 0, 2, 4])), score_tol=float(rng.choice([0.0, 0.0, 0.0, 0.05])),
+               center=int(rng.integers(0, J)))
+    jout = int(rng.integers(1, J + 1)) if rng.random() < 0.3 else J
+    pout = int(rng.integers(1, 6))
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout, keypoint_num=jout)
+    kp, sc, cn = _to_dev(torch, d["kpts"], d["scores"], d["counts"])
+    m = np.minimum(ref["nout"], pout)
+    valid = np.arange(pout)[None, :] < m[:, None]
+    for precision in ("f64", "mixed", "f32"):
+        eng = _engine(rig, prm, precision=precision)
+        if seed % 3 == 0:
+            eng.set_jit("always")
+        res = eng.run(kp, sc, cn, Pout=pout, keypoint_num=jout)
+        torch.cuda.synchronize()
+        out, nout = res["out"].cpu().numpy(), res["nout"].cpu().numpy()
+        tag = f"C={C} P={P} J={J} F={F} {precision} {prm} jout={jout} pout={pout} kernel={eng.last_launch_info()['kernel']}"
+        assert np.array_equal(nout, ref["nout"]), tag
+        assert not out[~valid].any(), tag
+        if valid.any():
+            assert np.array_equal(out[valid][:, :, 3] == 0, ref["kscores"][valid] == 0), tag
+            tol = TOL_FUSED if precision == "f64" else TOL_NORTH_STAR
+            assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol, tag
