@@ -31,6 +31,7 @@ WORKLOADS = {
     "cfg1": ("floor", 2, 1, 17, 1 << 20, "default", 1, "2 cameras, 1 person, 17 COCO keypoints (BASELINE configs[0])"),
     "cfg2": ("floor", 4, 1, 133, 1 << 17, "default", 1,
              "4 cameras (camera_group_floor.json calibration), 1 person, 133 Wholebody keypoints (BASELINE configs[1])"),
+    "c8p1": ("ring", 8, 1, 133, 1 << 16, "default", 1, "8 cameras, 1 person, 133 keypoints (single performer in a larger rig)"),
     "cfg3": ("ring", 8, 4, 133, 10000, "multi", 8, "8 cameras, 4 persons, 133 keypoints, 10k frames (BASELINE configs[2])"),
     "cfg4": ("ring", 16, 8, 133, 2000, "multi", 16,
              "16 cameras, 8 persons, 133 keypoints (BASELINE configs[3] geometry; 2000 frames per GPU per step)"),
