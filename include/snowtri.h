@@ -170,6 +170,43 @@ int snowtri_pack_ragged(snowtri_t* h, const float* d_det_kpts, const float* d_de
 int snowtri_dlt_run(snowtri_t* h, const float* d_kpts, const float* d_scores, int F, int J, float* d_out,
                     int accumulate_f64, void* stream);
 
+/* Blender control points (reference snowvision/blender.py; main.py:80-87 runs both steps on every frame).
+ *
+ * snowtri_blender_run = Human_Triangulation_Blender (blender.py:93-143, helpers :11-96): every person row of the
+ * snowtri_run / snowtri_condense output gives the 24 control points of configs/blender_armature_profile.json, in
+ * that file's order (0 root_position, 1 root_rotation, 2 clavicle_r_ik, 3 clavicle_l_ik, 4 arm_r_ik, 5 arm_r_pole,
+ * 6 arm_l_ik, 7 arm_l_pole, 8 leg_r_ik, 9 leg_r_pole, 10 leg_l_ik, 11 leg_l_pole, 12 hand_r_ik, 13 hand_r_pole,
+ * 14 hand_l_ik, 15 hand_l_pole, 16 foot_r_ik, 17 foot_r_pole, 18 foot_l_ik, 19 foot_l_pole, 20 chest_ik,
+ * 21 chest_pole, 22 head_ik, 23 head_pole):
+ *   d_points (F, Pout, J, 4) float32 (snowtri_run) or float64 (snowtri_condense): x, y, z, score; J >= 130
+ *   d_nout   (F) persons per frame, or NULL = every row holds a person; rows >= d_nout[f] give zeros / valid 0
+ *   d_ctrl   (F, Pout, 24, 4): (x, y, z, 0) for positions, (w, x, y, z) for root_rotation (blender.py:27)
+ *   d_valid  (F, Pout) uint32: bit k set = control point k has no NaN component = the reference's score 1
+ *            (blender.py:135-138).  The reference raises LinAlgError from SciPy on a NaN root rotation; the
+ *            batch call writes NaN and clears bit 1 instead.
+ * The arithmetic is float64 for both layouts. */
+int snowtri_blender_run(snowtri_t* h, const float* d_points, const int* d_nout, int F, int Pout, int J,
+                        float* d_ctrl, unsigned* d_valid, void* stream);
+int snowtri_blender_run_f64(snowtri_t* h, const double* d_points, const int* d_nout, int F, int Pout, int J,
+                            double* d_ctrl, unsigned* d_valid, void* stream);
+
+/* Human_Triangulation_Blender_Smooth (blender.py:145-178): one second-order follower (triangulation.py:4-22) per
+ * (person, control point), float64 state on the device so a clip can be streamed in batches of consecutive
+ * frames.  fzr (24,3) HOST array: f, z, r of every control point (configs/blender_smooth_profile.json).
+ * First frame of a clip: followers start at the control point (at zero where it is invalid), the frame passes
+ * through.  Later frames: persons are zipped by position with the first frame's followers (d_nsmooth[f] =
+ * min(d_nout[f], first frame's count)); a control point whose valid bit is 0 re-feeds the follower its previous
+ * input (blender.py:159-160).  d_ctrl is smoothed in place; d_valid passes through untouched. */
+typedef struct snowtri_blender_smooth_state snowtri_blender_smooth_t;
+int snowtri_blender_smooth_create(snowtri_t* h, snowtri_blender_smooth_t** out, int max_persons, const double* fzr);
+int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s);
+int snowtri_blender_smooth_reset(snowtri_t* h, snowtri_blender_smooth_t* s, void* stream);
+int snowtri_blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, float* d_ctrl, const unsigned* d_valid,
+                               const int* d_nout, int* d_nsmooth, int F, int Pout, double delta_time, void* stream);
+int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smooth_t* s, double* d_ctrl, const unsigned* d_valid,
+                                   const int* d_nout, int* d_nsmooth, int F, int Pout, double delta_time,
+                                   void* stream);
+
 /* Introspection. */
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */

@@ -34,6 +34,13 @@ SYMBOLS = {
     "snowtri_smooth_run_f64": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _D, _P]),
     "snowtri_pack_ragged": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "snowtri_dlt_run": (_I, [_P, _P, _P, _I, _I, _P, _I, _P]),
+    "snowtri_blender_run": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "snowtri_blender_run_f64": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "snowtri_blender_smooth_create": (_I, [_P, ct.POINTER(_P), _I, _P]),
+    "snowtri_blender_smooth_destroy": (_I, [_P]),
+    "snowtri_blender_smooth_reset": (_I, [_P, _P, _P]),
+    "snowtri_blender_smooth_run": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
+    "snowtri_blender_smooth_run_f64": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "snowtri_last_error": (ct.c_char_p, [_P]),
     "snowtri_launch_count": (ct.c_longlong, [_P]),
     "snowtri_last_launch_info": (_I, [_P, ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I)]),

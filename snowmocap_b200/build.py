@@ -13,7 +13,8 @@ LIB = os.path.join(PKG, "libsnowtri.so")
 OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = [os.path.join(CSRC, "snowtri_capi.cu"), os.path.join(CSRC, "snowtri_p1.cu"),
            os.path.join(CSRC, "snowtri_smooth.cu"), os.path.join(CSRC, "snowtri_general.cu"),
-           os.path.join(CSRC, "snowtri_jit.cu"), os.path.join(CSRC, "snowtri_dlt.cu")]
+           os.path.join(CSRC, "snowtri_jit.cu"), os.path.join(CSRC, "snowtri_dlt.cu"),
+           os.path.join(CSRC, "snowtri_blender.cu")]
 
 
 def _headers():

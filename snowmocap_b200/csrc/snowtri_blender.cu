@@ -1,0 +1,452 @@
+// Blender control points on the device: Human_Triangulation_Blender (reference
+// snowvision/blender.py:93-143 with its helpers :11-96) and Human_Triangulation_Blender_Smooth (:145-178),
+// the two steps main.py:80-87 runs on every frame after Human_Triangulation_Smooth.
+//
+// blender_kernel: one lane per person row of the snowtri_run / snowtri_condense output (F*Pout rows of J joints,
+// x y z score each).  A warp owns a tile of 32 rows.  Only 28 of the 133 joints are used (3..22 and eight hand
+// joints); the warp fetches them row by row -- lane l loads joint slot l, one 16/32-byte access each, the 20 body
+// joints of a row being contiguous -- and parks them transposed in shared memory ([slot][axis][row], odd pitch,
+// no bank conflicts either way), then every lane derives the 24 control points of its own row.  The arithmetic
+// is float64 for both layouts (the reference's, and cheap next to the memory traffic: ~0.9 KB moved per row).
+//
+// Root rotation (blender.py:15-36): the reference stacks the unit pelvis axis x, the unit spine axis y and
+// z = x X y / |x X y| as COLUMNS and hands that non-orthogonal matrix to SciPy, which replaces it by the
+// nearest rotation U V^T of its SVD (orthogonal Procrustes) before Markley's quaternion extraction.  For this
+// matrix the polar factor has a closed form: M^T M = [[1,c,0],[c,1,0],[0,0,1]] with c = x.y, so
+// U V^T = M (M^T M)^(-1/2) = [a x + b y | b x + a y | z],  a,b = (1/sqrt(1+c) +- 1/sqrt(1-c)) / 2
+// (symmetric orthogonalisation of x and y; z is already orthogonal to both).  No iteration, no SVD.
+// SciPy raises on a NaN matrix; the batch kernel writes NaN and clears the control point's valid bit instead
+// (the drop-in function raises like the reference, snowmocap_b200/blender.py).
+//
+// blender_smooth_kernel: one thread per (person, control point), four channels each, walking the frames of the
+// batch in order (the recurrence is sequential); per-control-point constants from the smooth profile; state
+// (xp, y, yd per channel, first-frame person count) stays on the device between calls.
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "snowtri_internal.h"
+
+#define SNOWTRI_NCTRL 24
+
+struct snowtri_blender_smooth_state {
+    int device, P;
+    double fzr[SNOWTRI_NCTRL * 3];
+    double* d_state;  // [0] initialised, [1] n0, then (P, 24, 12): xp[4], y[4], yd[4]
+};
+
+namespace snowtri {
+
+constexpr int kSlots = 28;   // joints a person row contributes
+constexpr int kPitch = 33;   // rows per tile + 1
+constexpr int kBlenderWarps = 2;
+
+// slot -> joint: slots 0..19 are joints 3..22, then the eight hand joints
+__device__ __forceinline__ int slot_joint(int s) {
+    // 91 palm_l, 96 index_l, 100 hand_l_ik, 108 pinky_l, 112 palm_r, 117 index_r, 121 hand_r_ik, 129 pinky_r
+    return s < 20 ? s + 3 : (s == 20 ? 91 : s == 21 ? 96 : s == 22 ? 100 : s == 23 ? 108 : s == 24 ? 112
+                             : s == 25 ? 117 : s == 26 ? 121 : 129);
+}
+__host__ __device__ constexpr int joint_slot(int j) {
+    return j <= 22 ? j - 3 : (j == 91 ? 20 : j == 96 ? 21 : j == 100 ? 22 : j == 108 ? 23 : j == 112 ? 24
+                              : j == 117 ? 25 : j == 121 ? 26 : 27);
+}
+
+struct BlenderArgs {
+    const void* pts;   // (rows, J, 4)
+    const int* nout;   // (F) or null: every row holds a person
+    void* ctrl;        // (rows, 24, 4)
+    unsigned* valid;   // (rows)
+    long long rows;
+    int Pout, J;
+};
+
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ D3 cross(D3 a, D3 b) {   // numpy.cross component order
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 unit(D3 a) {          // v / numpy.linalg.norm(v): 0/0 -> NaN like the reference
+    const double n = sqrt(dot(a, a));
+    return {a.x / n, a.y / n, a.z / n};
+}
+__device__ __forceinline__ D3 mid(D3 a, D3 b) { return (a + b) * 0.5; }
+__device__ __forceinline__ bool has_nan(D3 a) { return isnan(a.x) || isnan(a.y) || isnan(a.z); }
+
+// Get_Joint_Pole, blender.py:88-96
+__device__ __forceinline__ D3 joint_pole(D3 joint, D3 upper, D3 lower) {
+    const D3 a = upper - joint, b = lower - joint, c = upper - lower;
+    return joint + unit(cross(cross(b, a), c));
+}
+// Get_Hand_Pole / Get_Foot_Pole, blender.py:65-73, 78-86 (left: cross(second, first); right: cross(first, second))
+__device__ __forceinline__ D3 side_pole(D3 first, D3 second, D3 root, bool is_left) {
+    const D3 a = first - root, b = second - root;
+    return root + unit(is_left ? cross(b, a) : cross(a, b));
+}
+
+template <typename V>
+__device__ __forceinline__ void put(V* dst, int k, D3 v, unsigned& mask) {
+    V o;
+    o.x = (decltype(o.x))v.x;
+    o.y = (decltype(o.x))v.y;
+    o.z = (decltype(o.x))v.z;
+    o.w = 0;
+    dst[k] = o;
+    if (!has_nan(v)) mask |= 1u << k;
+}
+
+template <typename V>  // float4 (snowtri_run layout) or double4 (snowtri_condense layout)
+__global__ void __launch_bounds__(kBlenderWarps * 32) blender_kernel(const BlenderArgs a) {
+    using T = decltype(V().x);
+    __shared__ T sm[kBlenderWarps][kSlots * 3 * kPitch];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T* S = sm[warp];
+    const long long tiles = (a.rows + 31) / 32;
+    const V* __restrict__ pts = reinterpret_cast<const V*>(a.pts);
+    V* ctrl = reinterpret_cast<V*>(a.ctrl);
+    const int jl = slot_joint(lane < kSlots ? lane : 0);
+    for (long long tile = (long long)blockIdx.x * kBlenderWarps + warp; tile < tiles;
+         tile += (long long)gridDim.x * kBlenderWarps) {
+        const long long r0 = tile * 32;
+        const int nrows = (int)min(32LL, a.rows - r0);
+        // stage: lane = joint slot, loop over the rows of the tile (independent loads, all in flight together)
+        if (lane < kSlots) {
+#pragma unroll 8
+            for (int r = 0; r < nrows; ++r) {
+                const V p = pts[(size_t)(r0 + r) * a.J + jl];
+                S[(lane * 3 + 0) * kPitch + r] = p.x;
+                S[(lane * 3 + 1) * kPitch + r] = p.y;
+                S[(lane * 3 + 2) * kPitch + r] = p.z;
+            }
+        }
+        __syncwarp();
+        if (lane < nrows) {
+            const long long row = r0 + lane;
+            bool present = true;
+            if (a.nout) {
+                const long long f = row / a.Pout;
+                present = (int)(row - f * a.Pout) < a.nout[f];
+            }
+            V* dst = ctrl + (size_t)row * SNOWTRI_NCTRL;
+            unsigned mask = 0;
+            if (!present) {   // empty slot of the padded output: zeros, nothing valid
+                V zero;
+                zero.x = zero.y = zero.z = zero.w = 0;
+#pragma unroll
+                for (int k = 0; k < SNOWTRI_NCTRL; ++k) dst[k] = zero;
+            } else {
+                auto P = [&](int j) -> D3 {
+                    const int s = joint_slot(j) * 3;
+                    return {(double)S[(s + 0) * kPitch + lane], (double)S[(s + 1) * kPitch + lane],
+                            (double)S[(s + 2) * kPitch + lane]};
+                };
+                const D3 p3 = P(3), p4 = P(4), p5 = P(5), p6 = P(6), p11 = P(11), p12 = P(12);
+                const D3 pelvis_mid = mid(p11, p12), shoulder_mid = mid(p5, p6), ear_mid = mid(p3, p4);
+                const D3 spine = shoulder_mid - pelvis_mid, neck = ear_mid - shoulder_mid;
+                put(dst, 0, pelvis_mid, mask);                                  // root_position   :11-13
+                {                                                               // root_rotation   :15-36
+                    const D3 x = unit(p11 - p12), y = unit(spine), z = unit(cross(x, y));
+                    const double c = dot(x, y);
+                    const double ip = 1.0 / sqrt(1.0 + c), im = 1.0 / sqrt(1.0 - c);
+                    const double ca = 0.5 * (ip + im), cb = 0.5 * (ip - im);
+                    const D3 xo = x * ca + y * cb, yo = x * cb + y * ca;
+                    // rotation matrix m[i][j]: columns xo, yo, z
+                    const double m00 = xo.x, m10 = xo.y, m20 = xo.z, m01 = yo.x, m11 = yo.y, m21 = yo.z;
+                    const double m02 = z.x, m12 = z.y, m22 = z.z;
+                    const double tr = m00 + m11 + m22;
+                    double qx, qy, qz, qw;   // Markley: largest of (m00, m11, m22, trace), first wins ties
+                    int choice = 0;
+                    double best = m00;
+                    if (m11 > best) { best = m11; choice = 1; }
+                    if (m22 > best) { best = m22; choice = 2; }
+                    if (tr > best) { choice = 3; }
+                    if (choice == 0) {
+                        qx = 1.0 - tr + 2.0 * m00; qy = m10 + m01; qz = m20 + m02; qw = m21 - m12;
+                    } else if (choice == 1) {
+                        qx = m10 + m01; qy = 1.0 - tr + 2.0 * m11; qz = m21 + m12; qw = m02 - m20;
+                    } else if (choice == 2) {
+                        qx = m20 + m02; qy = m21 + m12; qz = 1.0 - tr + 2.0 * m22; qw = m10 - m01;
+                    } else {
+                        qx = m21 - m12; qy = m02 - m20; qz = m10 - m01; qw = 1.0 + tr;
+                    }
+                    const double qn = sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+                    V o;   // (w, x, y, z), blender.py:27
+                    o.x = (T)(qw / qn);
+                    o.y = (T)(qx / qn);
+                    o.z = (T)(qy / qn);
+                    o.w = (T)(qz / qn);
+                    dst[1] = o;
+                    if (!(isnan(qw / qn) || isnan(qx / qn) || isnan(qy / qn) || isnan(qz / qn))) mask |= 1u << 1;
+                }
+                put(dst, 2, p6, mask);                                          // clavicle_r_ik
+                put(dst, 3, p5, mask);                                          // clavicle_l_ik
+                const D3 p10 = P(10), p9 = P(9), p16 = P(16), p15 = P(15);
+                put(dst, 4, p10, mask);                                         // arm_r_ik
+                put(dst, 5, joint_pole(P(8), p6, p10), mask);                   // arm_r_pole
+                put(dst, 6, p9, mask);                                          // arm_l_ik
+                put(dst, 7, joint_pole(P(7), p5, p9), mask);                    // arm_l_pole
+                put(dst, 8, p16, mask);                                         // leg_r_ik
+                put(dst, 9, joint_pole(P(14), p12, p16), mask);                 // leg_r_pole
+                put(dst, 10, p15, mask);                                        // leg_l_ik
+                put(dst, 11, joint_pole(P(13), p11, p15), mask);                // leg_l_pole
+                put(dst, 12, P(121), mask);                                     // hand_r_ik
+                put(dst, 13, side_pole(P(117), P(129), P(112), false), mask);   // hand_r_pole
+                put(dst, 14, P(100), mask);                                     // hand_l_ik
+                put(dst, 15, side_pole(P(96), P(108), P(91), true), mask);      // hand_l_pole
+                const D3 p20 = P(20), p21 = P(21), p17 = P(17), p18 = P(18);
+                put(dst, 16, mid(p20, p21), mask);                              // foot_r_ik
+                put(dst, 17, side_pole(p20, p21, P(22), false), mask);          // foot_r_pole
+                put(dst, 18, mid(p17, p18), mask);                              // foot_l_ik
+                put(dst, 19, side_pole(p17, p18, P(19), true), mask);           // foot_l_pole
+                put(dst, 20, shoulder_mid, mask);                               // chest_ik        :38-40
+                put(dst, 21, shoulder_mid + unit(cross(p5 - p6, spine)), mask); // chest_pole      :42-48
+                put(dst, 22, shoulder_mid + unit(neck), mask);                  // head_ik         :50-55
+                put(dst, 23, ear_mid + unit(cross(p3 - p4, neck)), mask);       // head_pole       :57-63
+            }
+            a.valid[row] = mask;
+        }
+        __syncwarp();
+    }
+}
+
+struct BlenderSmoothArgs {
+    void* ctrl;             // (F, Pout, 24, 4), smoothed in place
+    const unsigned* valid;  // (F, Pout)
+    const int* nout;        // (F)
+    int* nsm;               // (F)
+    double* state;
+    int F, Pout, P;
+    double T, invT;
+    double k1[SNOWTRI_NCTRL], inv_k2[SNOWTRI_NCTRL], k3[SNOWTRI_NCTRL];
+};
+
+constexpr int kBsAhead = 4;
+
+template <typename V>
+__global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothArgs a) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = tid / SNOWTRI_NCTRL, c = tid - k * SNOWTRI_NCTRL;
+    if (k >= a.P) return;
+    const bool lead = tid == 0;
+    double* st = a.state + 2 + (size_t)tid * 12;
+    bool init = a.state[0] != 0.0;
+    int n0 = (int)a.state[1];
+    double xp[4], y[4], yd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        xp[i] = st[i];
+        y[i] = st[4 + i];
+        yd[i] = st[8 + i];
+    }
+    const double k1 = a.k1[c], inv_k2 = a.inv_k2[c], k3 = a.k3[c];
+    V* ctrl = reinterpret_cast<V*>(a.ctrl);
+    const bool inrange = k < a.Pout;
+    const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
+    const size_t base = (size_t)(inrange ? k : 0) * SNOWTRI_NCTRL + c;
+    const size_t vbase = inrange ? k : 0;
+    V buf[kBsAhead];
+    unsigned vb[kBsAhead];
+    int nb[kBsAhead];
+#pragma unroll
+    for (int u = 0; u < kBsAhead; ++u)
+        if (u < a.F) {
+            buf[u] = ctrl[(size_t)u * stride + base];
+            vb[u] = a.valid[(size_t)u * a.Pout + vbase];
+            nb[u] = a.nout[u];
+        }
+    for (int t0 = 0; t0 < a.F; t0 += kBsAhead) {
+#pragma unroll
+        for (int u = 0; u < kBsAhead; ++u) {
+            const int t = t0 + u;
+            if (t >= a.F) break;
+            const V p = buf[u];
+            const bool ok = (vb[u] >> c) & 1u;
+            const int n = min(max(nb[u], 0), a.Pout);
+            if (t + kBsAhead < a.F) {
+                buf[u] = ctrl[(size_t)(t + kBsAhead) * stride + base];
+                vb[u] = a.valid[(size_t)(t + kBsAhead) * a.Pout + vbase];
+                nb[u] = a.nout[t + kBsAhead];
+            }
+            const double x[4] = {(double)p.x, (double)p.y, (double)p.z, (double)p.w};
+            if (!init) {   // first frame of the clip (blender.py:165-176): followers start at the control point,
+                init = true;   // or at zero where it is invalid; the frame passes through
+                n0 = min(n, a.P);
+                if (k < n0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xp[i] = y[i] = ok ? x[i] : 0.0;
+                        yd[i] = 0.0;
+                    }
+                }
+                if (lead) a.nsm[t] = n;
+                continue;
+            }
+            const int m = min(n, n0);
+            if (lead) a.nsm[t] = m;
+            if (k < m) {   // blender.py:155-160 + triangulation.py:15-22; an invalid control point re-feeds xp
+                V o;
+                double out[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double xi = ok ? x[i] : xp[i];
+                    const double xd = (xi - xp[i]) * a.invT;
+                    xp[i] = xi;
+                    y[i] = y[i] + a.T * yd[i];
+                    yd[i] = yd[i] + a.T * (xi + k3 * xd - y[i] - k1 * yd[i]) * inv_k2;
+                    out[i] = y[i];
+                }
+                o.x = (decltype(o.x))out[0];
+                o.y = (decltype(o.x))out[1];
+                o.z = (decltype(o.x))out[2];
+                o.w = (decltype(o.x))out[3];
+                ctrl[(size_t)t * stride + base] = o;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        st[i] = xp[i];
+        st[4 + i] = y[i];
+        st[8 + i] = yd[i];
+    }
+    // every thread has read state[0..1] before any thread can get here only within a CTA; the flags are
+    // therefore rewritten by a separate tiny launch (blender_smooth_finish_kernel)
+}
+
+__global__ void blender_smooth_finish_kernel(double* state, const int* nout, int F, int Pout, int P) {
+    // replay the person-count bookkeeping of the batch: first frame of a clip fixes n0
+    if (threadIdx.x || blockIdx.x) return;
+    if (state[0] == 0.0 && F > 0) {
+        state[0] = 1.0;
+        state[1] = (double)min(min(max(nout[0], 0), Pout), P);
+    }
+}
+
+}  // namespace snowtri
+
+using namespace snowtri;
+
+static int blender_run(snowtri_t* h, const void* d_points, bool f64, const int* d_nout, int F, int Pout, int J,
+                       void* d_ctrl, unsigned* d_valid, void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_blender_run: NULL handle");
+    if (F < 0 || Pout < 0) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_run: bad argument");
+    if (F == 0 || Pout == 0) return SNOWTRI_OK;
+    if (!d_points || !d_ctrl || !d_valid) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_run: NULL buffer");
+    // the reference indexes person[129] (blender.py:103): fewer joints is its IndexError
+    if (J < 130) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_run: needs the Wholebody keypoints (J >= 130), got J=%d", J);
+    if ((((uintptr_t)d_points) & 15u) || (((uintptr_t)d_ctrl) & 15u))
+        return fail(h, SNOWTRI_E_ARG, "snowtri_blender_run: misaligned buffer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    BlenderArgs a;
+    a.pts = d_points; a.nout = d_nout; a.ctrl = d_ctrl; a.valid = d_valid;
+    a.rows = (long long)F * Pout; a.Pout = Pout; a.J = J;
+    const long long tiles = (a.rows + 31) / 32;
+    const long long want = (tiles + kBlenderWarps - 1) / kBlenderWarps;
+    const long long cap = (long long)h->sm_count * 16;   // persistent over tiles beyond 16 CTAs per SM
+    const unsigned blocks = (unsigned)(want < cap ? want : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64) blender_kernel<double4><<<blocks, kBlenderWarps * 32, 0, st>>>(a);
+    else blender_kernel<float4><<<blocks, kBlenderWarps * 32, 0, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_blender_run(snowtri_t* h, const float* d_points, const int* d_nout, int F, int Pout, int J,
+                                   float* d_ctrl, unsigned* d_valid, void* stream) {
+    return blender_run(h, d_points, false, d_nout, F, Pout, J, d_ctrl, d_valid, stream);
+}
+
+extern "C" int snowtri_blender_run_f64(snowtri_t* h, const double* d_points, const int* d_nout, int F, int Pout, int J,
+                                       double* d_ctrl, unsigned* d_valid, void* stream) {
+    return blender_run(h, d_points, true, d_nout, F, Pout, J, d_ctrl, d_valid, stream);
+}
+
+extern "C" int snowtri_blender_smooth_create(snowtri_t* h, snowtri_blender_smooth_t** out, int max_persons,
+                                             const double* fzr) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_blender_smooth_create: NULL handle");
+    if (!out || !fzr || max_persons < 1) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_create: bad argument");
+    for (int c = 0; c < SNOWTRI_NCTRL; ++c)
+        if (!(fzr[3 * c] > 0.0))   // the reference divides by f (triangulation.py:7-9)
+            return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_create: f must be positive (control point %d)", c);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    snowtri_blender_smooth_t* s = (snowtri_blender_smooth_t*)calloc(1, sizeof(*s));
+    if (!s) return fail(h, SNOWTRI_E_NOMEM, "snowtri_blender_smooth_create: out of host memory");
+    s->device = h->device;
+    s->P = max_persons;
+    memcpy(s->fzr, fzr, sizeof(s->fzr));
+    const size_t bytes = (2 + (size_t)max_persons * SNOWTRI_NCTRL * 12) * sizeof(double);
+    cudaError_t e = cudaMalloc(&s->d_state, bytes);
+    if (e == cudaSuccess) e = cudaMemset(s->d_state, 0, bytes);
+    if (e != cudaSuccess) {
+        if (s->d_state) cudaFree(s->d_state);
+        free(s);
+        return fail(h, SNOWTRI_E_CUDA, "snowtri_blender_smooth_create: %s", cudaGetErrorString(e));
+    }
+    *out = s;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s) {
+    if (!s) return SNOWTRI_OK;
+    cudaSetDevice(s->device);
+    cudaFree(s->d_state);
+    free(s);
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_blender_smooth_reset(snowtri_t* h, snowtri_blender_smooth_t* s, void* stream) {
+    if (!h || !s) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_reset: NULL argument");
+    CUDA_TRY(h, cudaSetDevice(s->device));
+    CUDA_TRY(h, cudaMemsetAsync(s->d_state, 0, (2 + (size_t)s->P * SNOWTRI_NCTRL * 12) * sizeof(double),
+                                (cudaStream_t)stream));
+    return SNOWTRI_OK;
+}
+
+static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d_ctrl, bool f64, const unsigned* d_valid,
+                              const int* d_nout, int* d_nsm, int F, int Pout, double delta_time, void* stream) {
+    if (!h || !s) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_run: NULL argument");
+    if (F < 0 || Pout < 1 || !(delta_time > 0.0)) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_run: bad argument");
+    if (F == 0) return SNOWTRI_OK;
+    if (!d_ctrl || !d_valid || !d_nout || !d_nsm) return fail(h, SNOWTRI_E_ARG, "snowtri_blender_smooth_run: NULL buffer");
+    CUDA_TRY(h, cudaSetDevice(s->device));
+    BlenderSmoothArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ctrl = d_ctrl; a.valid = d_valid; a.nout = d_nout; a.nsm = d_nsm; a.state = s->d_state;
+    a.F = F; a.Pout = Pout; a.P = s->P;
+    a.T = delta_time; a.invT = 1.0 / delta_time;
+    const double pi = 3.141592653589793;   // math.pi
+    for (int c = 0; c < SNOWTRI_NCTRL; ++c) {   // triangulation.py:7-9
+        const double f = s->fzr[3 * c], z = s->fzr[3 * c + 1], r = s->fzr[3 * c + 2];
+        a.k1[c] = z / (pi * f);
+        a.inv_k2[c] = 1.0 / (1.0 / ((2 * pi * f) * (2 * pi * f)));
+        a.k3[c] = r * z / (2 * pi * f);
+    }
+    const int threads = s->P * SNOWTRI_NCTRL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (f64) blender_smooth_kernel<double4><<<(threads + 95) / 96, 96, 0, st>>>(a);
+    else blender_smooth_kernel<float4><<<(threads + 95) / 96, 96, 0, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    blender_smooth_finish_kernel<<<1, 32, 0, st>>>(s->d_state, d_nout, F, Pout, s->P);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 2;
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, float* d_ctrl,
+                                          const unsigned* d_valid, const int* d_nout, int* d_nsmooth, int F, int Pout,
+                                          double delta_time, void* stream) {
+    return blender_smooth_run(h, s, d_ctrl, false, d_valid, d_nout, d_nsmooth, F, Pout, delta_time, stream);
+}
+
+extern "C" int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smooth_t* s, double* d_ctrl,
+                                              const unsigned* d_valid, const int* d_nout, int* d_nsmooth, int F,
+                                              int Pout, double delta_time, void* stream) {
+    return blender_smooth_run(h, s, d_ctrl, true, d_valid, d_nout, d_nsmooth, F, Pout, delta_time, stream);
+}

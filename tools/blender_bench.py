@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Time the Blender control-point stage (snowtri_blender_run, snowtri_blender_smooth_run) on the cfg2 output shape
+(131 072 frames x 1 person x 133 joints, float32 x y z score) and report the HBM roofline of blender_kernel.
+
+Algorithmic bytes per person row: 28 joints x 12 B (x, y, z) read + 24 control points x 16 B + 4 B valid mask written
+= 724 B.  With the (x, y, z, score) float4 layout and 32-byte sectors the kernel cannot fetch fewer than about
+608 B per row (a 320-byte body block + eight scattered hand joints), i.e. ~996 B of DRAM traffic per row."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from snowmocap_b200.blender import BlenderControl, BlenderSmoothState  # noqa: E402
+from snowmocap_b200.triangulation import _util_engine  # noqa: E402
+
+F, P, J = int(os.environ.get("BLENDER_BENCH_F", 131072)), int(os.environ.get("BLENDER_BENCH_P", 1)), 133
+STEPS = 20
+eng = _util_engine()
+dev = torch.device("cuda", 0)
+g = torch.Generator(device=dev).manual_seed(7)
+out = torch.rand((F, P, J, 4), generator=g, device=dev) * 2.0
+nout = torch.full((F,), P, dtype=torch.int32, device=dev)
+try:
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    peak = 6650.0
+bc = BlenderControl(eng)
+
+
+def timed(fn, steps=STEPS, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+ms = timed(lambda: bc.run(out, nout))
+rows = F * P
+gbs = 724 * rows / (ms * 1e-3) / 1e9
+ctrl, valid = bc.run(out, nout)
+fzr = [[2.5, 0.75, 0.0]] * 24
+st = BlenderSmoothState(eng, P, fzr)
+
+
+def smooth():
+    st.reset()
+    st.run(ctrl, valid, nout, 1 / 30)
+
+
+ms_s = timed(smooth, steps=5, warm=2)
+print(json.dumps({"op": "snowtri_blender_run", "F": F, "Pout": P, "J": J, "dtype": "f32 layout, f64 arithmetic",
+                  "ms": ms, "persons_per_s": rows / (ms * 1e-3), "algorithmic_bytes_per_row": 724,
+                  "algorithmic_GBs": gbs, "peak_GBs": peak, "frac_of_measured_hbm": gbs / peak,
+                  "input_bytes": out.numel() * 4, "timing": "input larger than L2" if out.numel() * 4 > 126e6 else "input fits L2",
+                  "smooth": {"op": "snowtri_blender_smooth_run (sequential over frames)", "ms": ms_s,
+                             "frames_per_s": F / (ms_s * 1e-3), "ns_per_frame_step": ms_s * 1e6 / F}}))

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Blender control-point stage on the GPU box: parity tests, timings, launch list and one full ncu capture.
+# Usage (through gpurun): bash tools/gpu_blender.sh [tag]
+tag=${1:-blender}
+out=gpurun_out/$tag
+mkdir -p $out
+timeout 600 python -m pytest tests/test_blender.py -m gpu -x -q > $out/pytest_blender.log 2>&1; echo "pytest rc=$?" >> $out/pytest_blender.log
+tail -15 $out/pytest_blender.log
+timeout 300 python tools/blender_bench.py > $out/blender_bench.json 2> $out/blender_bench.err; cat $out/blender_bench.json; tail -3 $out/blender_bench.err
+BLENDER_BENCH_P=8 timeout 300 python tools/blender_bench.py > $out/blender_bench_p8.json 2> $out/blender_bench_p8.err; cat $out/blender_bench_p8.json
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:blender -c 40 --csv --log-file $out/launches_blender.csv \
+    python tools/blender_bench.py > $out/ncu_launches_blender.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:blender_kernel -s 3 -c 1 -f -o $out/blender_kernel_f32 \
+    python tools/blender_bench.py > $out/ncu_full_blender.log 2>&1
+tail -2 $out/ncu_full_blender.log | cut -c1-200
