@@ -201,6 +201,9 @@ typedef struct snowtri_blender_smooth_state snowtri_blender_smooth_t;
 int snowtri_blender_smooth_create(snowtri_t* h, snowtri_blender_smooth_t** out, int max_persons, const double* fzr);
 int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s);
 int snowtri_blender_smooth_reset(snowtri_t* h, snowtri_blender_smooth_t* s, void* stream);
+/* Batches of more than 256 frames are cut into 128-frame chunks that run in parallel (every chunk is an affine map
+ * of its start state; the maps are chained by a short sequential pass); enabled = 0 forces the sequential kernel. */
+int snowtri_blender_smooth_set_chunked(snowtri_blender_smooth_t* s, int enabled);
 int snowtri_blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, float* d_ctrl, const unsigned* d_valid,
                                const int* d_nout, int* d_nsmooth, int F, int Pout, double delta_time, void* stream);
 int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smooth_t* s, double* d_ctrl, const unsigned* d_valid,

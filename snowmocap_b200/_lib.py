@@ -39,6 +39,7 @@ SYMBOLS = {
     "snowtri_blender_smooth_create": (_I, [_P, ct.POINTER(_P), _I, _P]),
     "snowtri_blender_smooth_destroy": (_I, [_P]),
     "snowtri_blender_smooth_reset": (_I, [_P, _P, _P]),
+    "snowtri_blender_smooth_set_chunked": (_I, [_P, _I]),
     "snowtri_blender_smooth_run": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "snowtri_blender_smooth_run_f64": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "snowtri_last_error": (ct.c_char_p, [_P]),

@@ -77,6 +77,10 @@ class BlenderSmoothState:
             _lib.check(self._lib.snowtri_blender_smooth_create(engine._h, ct.byref(self._s), self.max_persons,
                                                                self._fzr.ctypes.data), engine._h)
 
+    def set_chunked(self, enabled=True):
+        """Long batches run as parallel 128-frame chunks (default); False forces the sequential kernel."""
+        _lib.check(self._lib.snowtri_blender_smooth_set_chunked(self._s, 1 if enabled else 0), self._eng._h)
+
     def reset(self):
         _lib.check(self._lib.snowtri_blender_smooth_reset(self._eng._h, self._s, _stream()), self._eng._h)
 

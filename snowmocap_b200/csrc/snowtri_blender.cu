@@ -29,11 +29,20 @@
 #include "snowtri_internal.h"
 
 #define SNOWTRI_NCTRL 24
+#ifndef BLENDER_MINB
+#define BLENDER_MINB 8   // CTAs per SM the register budget is capped for (64-thread CTAs: 128 registers)
+#endif
+#ifndef BLENDER_UNROLL
+#define BLENDER_UNROLL 16   // row loads in flight per lane while staging a tile
+#endif
 
 struct snowtri_blender_smooth_state {
     int device, P;
     double fzr[SNOWTRI_NCTRL * 3];
     double* d_state;  // [0] initialised, [1] n0, then (P, 24, 12): xp[4], y[4], yd[4]
+    double* d_work;   // chunk-parallel path: per chunk 33 values per (person, control point), see kBsWork
+    size_t work_chunks;
+    int sequential;   // 1 = always the single-launch sequential kernel
 };
 
 namespace snowtri {
@@ -41,6 +50,7 @@ namespace snowtri {
 constexpr int kSlots = 28;   // joints a person row contributes
 constexpr int kPitch = 33;   // rows per tile + 1
 constexpr int kBlenderWarps = 2;
+constexpr int kStageUnroll = BLENDER_UNROLL;
 
 // slot -> joint: slots 0..19 are joints 3..22, then the eight hand joints
 __device__ __forceinline__ int slot_joint(int s) {
@@ -102,7 +112,7 @@ __device__ __forceinline__ void put(V* dst, int k, D3 v, unsigned& mask) {
 }
 
 template <typename V>  // float4 (snowtri_run layout) or double4 (snowtri_condense layout)
-__global__ void __launch_bounds__(kBlenderWarps * 32) blender_kernel(const BlenderArgs a) {
+__global__ void __launch_bounds__(kBlenderWarps * 32, BLENDER_MINB) blender_kernel(const BlenderArgs a) {
     using T = decltype(V().x);
     __shared__ T sm[kBlenderWarps][kSlots * 3 * kPitch];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -117,7 +127,7 @@ __global__ void __launch_bounds__(kBlenderWarps * 32) blender_kernel(const Blend
         const int nrows = (int)min(32LL, a.rows - r0);
         // stage: lane = joint slot, loop over the rows of the tile (independent loads, all in flight together)
         if (lane < kSlots) {
-#pragma unroll 8
+#pragma unroll kStageUnroll
             for (int r = 0; r < nrows; ++r) {
                 const V p = pts[(size_t)(r0 + r) * a.J + jl];
                 S[(lane * 3 + 0) * kPitch + r] = p.x;
@@ -319,6 +329,182 @@ __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothA
     // therefore rewritten by a separate tiny launch (blender_smooth_finish_kernel)
 }
 
+// ---- chunk-parallel path for long batches --------------------------------------------------------------------
+// One step of a follower is affine in its state s = (xp, y, yd): with a valid control point s' = A1 s + b1 x, with
+// an invalid one (the follower is fed its own xp) s' = A0 s, for an absent person s' = s.  So a chunk of frames
+// acts on its start state as s_end = M s_start + b, where M (3x3, shared by the four channels of a control point)
+// depends only on the valid/absent pattern of the chunk and b on the inputs:
+//   pass A  every (chunk, person, control point) thread runs the chunk from a ZERO state with the real inputs (-> b,
+//           four channels) and from the three unit states with zero inputs (-> the columns of M).  Chunk 0 knows
+//           its true start (the stored state, or the seeding first frame of a clip), so it runs for real, writes
+//           its outputs and leaves its end state in b;
+//   pass B  per (person, control point), sequentially over the chunks: start_c = M_(c-1) start_(c-1) + b_(c-1);
+//   pass C  every chunk >= 1 runs again from its true start state and writes the smoothed control points.
+// Inside a chunk the arithmetic is the reference's recurrence; only the hand-over between chunks is evaluated
+// differently (agreement with the sequential kernel ~1e-15 relative).
+constexpr int kBsChunk = 128;
+constexpr int kBsWork = 33;   // per (chunk, thread): M (9), b (4 channels x 3), start (4 channels x 3)
+
+struct BsChunkArgs {
+    BlenderSmoothArgs s;
+    double* work;   // [(chunk * kBsWork + i) * NT + tid]
+    int nchunks, NT;
+};
+
+__device__ __forceinline__ void bs_step(const BlenderSmoothArgs& a, double k1, double inv_k2, double k3, bool ok,
+                                        double x, double& xp, double& y, double& yd) {
+    const double xi = ok ? x : xp;   // blender.py:157-160
+    const double xd = (xi - xp) * a.invT;   // triangulation.py:15-22
+    xp = xi;
+    y = y + a.T * yd;
+    yd = yd + a.T * (xi + k3 * xd - y - k1 * yd) * inv_k2;
+}
+
+template <typename V, int PASS>   // PASS 0 = A, 2 = C
+__global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkArgs ca) {
+    const BlenderSmoothArgs& a = ca.s;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunk = gtid / ca.NT + (PASS == 2 ? 1 : 0), tid = gtid % ca.NT;
+    if (chunk >= ca.nchunks) return;
+    const int k = tid / SNOWTRI_NCTRL, c = tid - k * SNOWTRI_NCTRL;
+    const bool was_init = a.state[0] != 0.0;
+    const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
+    const double k1 = a.k1[c], inv_k2 = a.inv_k2[c], k3 = a.k3[c];
+    V* ctrl = reinterpret_cast<V*>(a.ctrl);
+    const bool inrange = k < a.Pout;
+    const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
+    const size_t base = (size_t)(inrange ? k : 0) * SNOWTRI_NCTRL + c;
+    const size_t vbase = inrange ? k : 0;
+    const int t_begin = chunk * kBsChunk, t_end = min(a.F, t_begin + kBsChunk);
+    double* w = ca.work + (size_t)chunk * kBsWork * ca.NT + tid;
+    const bool real = PASS == 2 || chunk == 0;   // runs from the true start state and writes outputs
+    double xp[4], y[4], yd[4];
+    double bx[3] = {1.0, 0.0, 0.0}, by[3] = {0.0, 1.0, 0.0}, bd[3] = {0.0, 0.0, 1.0};   // unit states (pass A)
+    if (PASS == 2) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xp[i] = w[(size_t)(21 + 3 * i + 0) * ca.NT];
+            y[i] = w[(size_t)(21 + 3 * i + 1) * ca.NT];
+            yd[i] = w[(size_t)(21 + 3 * i + 2) * ca.NT];
+        }
+    } else if (chunk == 0) {
+        const double* st = a.state + 2 + (size_t)tid * 12;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            xp[i] = st[i];
+            y[i] = st[4 + i];
+            yd[i] = st[8 + i];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xp[i] = y[i] = yd[i] = 0.0;
+    }
+    bool init = was_init || chunk > 0;
+    V buf[kBsAhead];
+    unsigned vb[kBsAhead];
+    int nb[kBsAhead];
+#pragma unroll
+    for (int u = 0; u < kBsAhead; ++u)
+        if (t_begin + u < t_end) {
+            buf[u] = ctrl[(size_t)(t_begin + u) * stride + base];
+            vb[u] = a.valid[(size_t)(t_begin + u) * a.Pout + vbase];
+            nb[u] = a.nout[t_begin + u];
+        }
+    for (int t0 = t_begin; t0 < t_end; t0 += kBsAhead) {
+#pragma unroll
+        for (int u = 0; u < kBsAhead; ++u) {
+            const int t = t0 + u;
+            if (t >= t_end) break;
+            const V p = buf[u];
+            const bool ok = (vb[u] >> c) & 1u;
+            const int n = min(max(nb[u], 0), a.Pout);
+            if (t + kBsAhead < t_end) {
+                buf[u] = ctrl[(size_t)(t + kBsAhead) * stride + base];
+                vb[u] = a.valid[(size_t)(t + kBsAhead) * a.Pout + vbase];
+                nb[u] = a.nout[t + kBsAhead];
+            }
+            const double x[4] = {(double)p.x, (double)p.y, (double)p.z, (double)p.w};
+            if (!init) {   // only chunk 0 of a new clip: the seeding frame (blender.py:165-176)
+                init = true;
+                if (k < n0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        xp[i] = y[i] = ok ? x[i] : 0.0;
+                        yd[i] = 0.0;
+                    }
+                }
+                if (PASS == 0 && tid == 0) a.nsm[t] = n;
+                continue;
+            }
+            const int m = min(n, n0);
+            if (PASS == 0 && tid == 0) a.nsm[t] = m;
+            if (k < m) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bs_step(a, k1, inv_k2, k3, ok, x[i], xp[i], y[i], yd[i]);
+                if (real) {
+                    V o;
+                    o.x = (decltype(o.x))y[0];
+                    o.y = (decltype(o.x))y[1];
+                    o.z = (decltype(o.x))y[2];
+                    o.w = (decltype(o.x))y[3];
+                    ctrl[(size_t)t * stride + base] = o;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) bs_step(a, k1, inv_k2, k3, ok, 0.0, bx[j], by[j], bd[j]);
+                }
+            }
+        }
+    }
+    if (PASS == 0) {
+        // M column j = image of unit state j: rows (xp, y, yd)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[(size_t)(0 + j) * ca.NT] = bx[j];
+            w[(size_t)(3 + j) * ca.NT] = by[j];
+            w[(size_t)(6 + j) * ca.NT] = bd[j];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            w[(size_t)(9 + 3 * i + 0) * ca.NT] = xp[i];
+            w[(size_t)(9 + 3 * i + 1) * ca.NT] = y[i];
+            w[(size_t)(9 + 3 * i + 2) * ca.NT] = yd[i];
+        }
+    }
+}
+
+// pass B: start states of chunks 1.., then the state after the last chunk goes back to the persistent state
+__global__ void __launch_bounds__(96) blender_smooth_carry_kernel(const BsChunkArgs ca) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= ca.NT) return;
+    double s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = ca.work[(size_t)(9 + i) * ca.NT + tid];   // end state of chunk 0
+    for (int chunk = 1; chunk < ca.nchunks; ++chunk) {
+        double* w = ca.work + (size_t)chunk * kBsWork * ca.NT + tid;
+        double M[9], b[12];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i] = w[(size_t)i * ca.NT];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) b[i] = w[(size_t)(9 + i) * ca.NT];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[(size_t)(21 + i) * ca.NT] = s[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double s0 = s[3 * i], s1 = s[3 * i + 1], s2 = s[3 * i + 2];
+            s[3 * i + 0] = b[3 * i + 0] + (M[0] * s0 + M[1] * s1 + M[2] * s2);
+            s[3 * i + 1] = b[3 * i + 1] + (M[3] * s0 + M[4] * s1 + M[5] * s2);
+            s[3 * i + 2] = b[3 * i + 2] + (M[6] * s0 + M[7] * s1 + M[8] * s2);
+        }
+    }
+    double* st = ca.s.state + 2 + (size_t)tid * 12;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        st[i] = s[3 * i];
+        st[4 + i] = s[3 * i + 1];
+        st[8 + i] = s[3 * i + 2];
+    }
+}
+
 __global__ void blender_smooth_finish_kernel(double* state, const int* nout, int F, int Pout, int P) {
     // replay the person-count bookkeeping of the batch: first frame of a clip fixes n0
     if (threadIdx.x || blockIdx.x) return;
@@ -397,7 +583,14 @@ extern "C" int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s) {
     if (!s) return SNOWTRI_OK;
     cudaSetDevice(s->device);
     cudaFree(s->d_state);
+    if (s->d_work) cudaFree(s->d_work);
     free(s);
+    return SNOWTRI_OK;
+}
+
+extern "C" int snowtri_blender_smooth_set_chunked(snowtri_blender_smooth_t* s, int enabled) {
+    if (!s) return SNOWTRI_E_ARG;
+    s->sequential = enabled ? 0 : 1;
     return SNOWTRI_OK;
 }
 
@@ -430,12 +623,37 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
     }
     const int threads = s->P * SNOWTRI_NCTRL;
     cudaStream_t st = (cudaStream_t)stream;
-    if (f64) blender_smooth_kernel<double4><<<(threads + 95) / 96, 96, 0, st>>>(a);
-    else blender_smooth_kernel<float4><<<(threads + 95) / 96, 96, 0, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
+    if (s->sequential || F <= 2 * kBsChunk) {
+        if (f64) blender_smooth_kernel<double4><<<(threads + 95) / 96, 96, 0, st>>>(a);
+        else blender_smooth_kernel<float4><<<(threads + 95) / 96, 96, 0, st>>>(a);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+    } else {
+        BsChunkArgs ca;
+        ca.s = a;
+        ca.nchunks = (F + kBsChunk - 1) / kBsChunk;
+        ca.NT = threads;
+        if (s->work_chunks < (size_t)ca.nchunks) {
+            CUDA_TRY(h, cudaStreamSynchronize(st));   // an earlier batch may still be using the old buffer
+            if (s->d_work) cudaFree(s->d_work);
+            s->d_work = nullptr;
+            s->work_chunks = 0;
+            CUDA_TRY(h, cudaMalloc(&s->d_work, (size_t)ca.nchunks * kBsWork * threads * sizeof(double)));
+            s->work_chunks = (size_t)ca.nchunks;
+        }
+        ca.work = s->d_work;
+        const long long ta = (long long)ca.nchunks * threads, tc = (long long)(ca.nchunks - 1) * threads;
+        if (f64) blender_smooth_chunk_kernel<double4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
+        else blender_smooth_chunk_kernel<float4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
+        blender_smooth_carry_kernel<<<(threads + 95) / 96, 96, 0, st>>>(ca);
+        if (f64) blender_smooth_chunk_kernel<double4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
+        else blender_smooth_chunk_kernel<float4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 3;
+    }
     blender_smooth_finish_kernel<<<1, 32, 0, st>>>(s->d_state, d_nout, F, Pout, s->P);
     CUDA_TRY(h, cudaGetLastError());
-    h->launches += 2;
+    h->launches += 1;
     return SNOWTRI_OK;
 }
 

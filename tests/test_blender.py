@@ -299,8 +299,11 @@ def test_batch_clip_matches_reference_golden(torch_cuda, dtype, tol, split):
 
 
 @pytest.mark.gpu
-def test_batch_smooth_long_clip_vs_oracle(torch_cuda):
-    """600 frames, person count changing, random invalid control points, non-zero r."""
+@pytest.mark.parametrize("chunked,batches", [(True, [600]), (False, [600]), (True, [290, 310]), (True, [1, 599]),
+                                             (True, [300, 40, 260])])
+def test_batch_smooth_long_clip_vs_oracle(torch_cuda, chunked, batches):
+    """600 frames, person count changing, random invalid control points, non-zero r; the chunk-parallel path
+    (batches of more than 256 frames), the sequential kernel, and a clip streamed through both."""
     torch = torch_cuda
     from snowmocap_b200.blender import BlenderSmoothState
     rng = np.random.default_rng(77)
@@ -318,10 +321,15 @@ def test_batch_smooth_long_clip_vs_oracle(torch_cuda):
     eng = _util_engine()
     c = torch.from_numpy(ctrl.copy()).cuda()
     state = BlenderSmoothState(eng, P, fzr)
-    nsm = state.run(c, torch.from_numpy(vbits).cuda(), torch.from_numpy(nout).cuda(), 1 / 30)
+    state.set_chunked(chunked)
+    vb, no = torch.from_numpy(vbits).cuda(), torch.from_numpy(nout).cuda()
+    nsm, s0 = [], 0
+    for n in batches:
+        nsm.append(state.run(c[s0:s0 + n], vb[s0:s0 + n], no[s0:s0 + n], 1 / 30))
+        s0 += n
     torch.cuda.synchronize()
     got = c.cpu().numpy()
-    assert np.array_equal(nsm.cpu().numpy(), nout)
+    assert np.array_equal(torch.cat(nsm).cpu().numpy(), nout)
     for t in range(F):
         m = nout[t]
         assert np.array_equal(np.isnan(got[t, :m]), np.isnan(want[t])), t

@@ -56,10 +56,15 @@ def smooth():
     st.run(ctrl, valid, nout, 1 / 30)
 
 
-ms_s = timed(smooth, steps=5, warm=2)
+res_s = {}
+if not os.environ.get("BLENDER_BENCH_NO_SMOOTH"):
+    for name, chunked in (("chunked", True), ("sequential", False)):
+        st.set_chunked(chunked)
+        ms_s = timed(smooth, steps=5, warm=2)
+        res_s[name] = {"ms": ms_s, "frames_per_s": F / (ms_s * 1e-3), "ns_per_frame_step": ms_s * 1e6 / F}
 print(json.dumps({"op": "snowtri_blender_run", "F": F, "Pout": P, "J": J, "dtype": "f32 layout, f64 arithmetic",
                   "ms": ms, "persons_per_s": rows / (ms * 1e-3), "algorithmic_bytes_per_row": 724,
                   "algorithmic_GBs": gbs, "peak_GBs": peak, "frac_of_measured_hbm": gbs / peak,
                   "input_bytes": out.numel() * 4, "timing": "input larger than L2" if out.numel() * 4 > 126e6 else "input fits L2",
-                  "smooth": {"op": "snowtri_blender_smooth_run (sequential over frames)", "ms": ms_s,
-                             "frames_per_s": F / (ms_s * 1e-3), "ns_per_frame_step": ms_s * 1e6 / F}}))
+                  "nvcc_flags": os.environ.get("SNOWTRI_NVCC_FLAGS", ""),
+                  "smooth": {"op": "snowtri_blender_smooth_run (reset + one batch of F frames)", **res_s}}))
