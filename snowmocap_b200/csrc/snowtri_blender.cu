@@ -30,7 +30,7 @@
 
 #define SNOWTRI_NCTRL 24
 #ifndef BLENDER_MINB
-#define BLENDER_MINB 8   // CTAs per SM the register budget is capped for (64-thread CTAs: 128 registers)
+#define BLENDER_MINB 6   // CTAs per SM the register budget is capped for (measured: 6 x 16 best, tools/gpu_blender.sh)
 #endif
 #ifndef BLENDER_UNROLL
 #define BLENDER_UNROLL 16   // row loads in flight per lane while staging a tile
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothA
 //           four channels) and from the three unit states with zero inputs (-> the columns of M).  Chunk 0 knows
 //           its true start (the stored state, or the seeding first frame of a clip), so it runs for real, writes
 //           its outputs and leaves its end state in b;
-//   pass B  per (person, control point), sequentially over the chunks: start_c = M_(c-1) start_(c-1) + b_(c-1);
+//   pass B  start_c = M_(c-1) start_(c-1) + b_(c-1) along the chunks, as a two-level chain (groups of 32 chunks);
 //   pass C  every chunk >= 1 runs again from its true start state and writes the smoothed control points.
 // Inside a chunk the arithmetic is the reference's recurrence; only the hand-over between chunks is evaluated
 // differently (agreement with the sequential kernel ~1e-15 relative).
@@ -458,10 +458,10 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
     if (PASS == 0) {
         // M column j = image of unit state j: rows (xp, y, yd)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            w[(size_t)(0 + j) * ca.NT] = bx[j];
-            w[(size_t)(3 + j) * ca.NT] = by[j];
-            w[(size_t)(6 + j) * ca.NT] = bd[j];
+        for (int j = 0; j < 3; ++j) {   // chunk 0 ran from its true start: its end state does not depend on start_0
+            w[(size_t)(0 + j) * ca.NT] = chunk == 0 ? 0.0 : bx[j];
+            w[(size_t)(3 + j) * ca.NT] = chunk == 0 ? 0.0 : by[j];
+            w[(size_t)(6 + j) * ca.NT] = chunk == 0 ? 0.0 : bd[j];
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -472,29 +472,78 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
     }
 }
 
-// pass B: start states of chunks 1.., then the state after the last chunk goes back to the persistent state
-__global__ void __launch_bounds__(96) blender_smooth_carry_kernel(const BsChunkArgs ca) {
+// pass B, three short launches over groups of kBsGroup chunks (chunk 0 carries M = 0 and b = its true end state,
+// so the chain start_(c+1) = M_c start_c + b_c holds for every chunk from an arbitrary start_0):
+//   B1  every (group, person, control point) composes the maps of its chunks into one map (Mg, bg);
+//   B2  per (person, control point), sequentially over the groups: start state of every group; the state after the
+//       last group goes back to the persistent state;
+//   B3  every (group, person, control point) walks its chunks again from the group's start state and leaves
+//       start_c for pass C.
+constexpr int kBsGroup = 32;
+
+struct Affine {   // s -> M s + b for the four channels of a control point
+    double M[9], b[12];
+};
+__device__ __forceinline__ void affine_load(Affine& f, const double* w, int NT) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f.M[i] = w[(size_t)i * NT];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) f.b[i] = w[(size_t)(9 + i) * NT];
+}
+__device__ __forceinline__ void affine_apply(const Affine& f, double* s) {   // s (4 channels x 3) <- M s + b
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double s0 = s[3 * i], s1 = s[3 * i + 1], s2 = s[3 * i + 2];
+        s[3 * i + 0] = f.b[3 * i + 0] + (f.M[0] * s0 + f.M[1] * s1 + f.M[2] * s2);
+        s[3 * i + 1] = f.b[3 * i + 1] + (f.M[3] * s0 + f.M[4] * s1 + f.M[5] * s2);
+        s[3 * i + 2] = f.b[3 * i + 2] + (f.M[6] * s0 + f.M[7] * s1 + f.M[8] * s2);
+    }
+}
+
+__global__ void __launch_bounds__(96) blender_smooth_carry_compose_kernel(const BsChunkArgs ca, double* gwork, int ngroups) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = gtid / ca.NT, tid = gtid % ca.NT;
+    if (g >= ngroups) return;
+    const int c0 = g * kBsGroup, c1 = min(ca.nchunks, c0 + kBsGroup);
+    Affine acc, cur, nxt;
+    affine_load(acc, ca.work + (size_t)c0 * kBsWork * ca.NT + tid, ca.NT);
+    if (c0 + 1 < c1) affine_load(nxt, ca.work + (size_t)(c0 + 1) * kBsWork * ca.NT + tid, ca.NT);
+    for (int c = c0 + 1; c < c1; ++c) {
+        cur = nxt;
+        if (c + 1 < c1) affine_load(nxt, ca.work + (size_t)(c + 1) * kBsWork * ca.NT + tid, ca.NT);
+        // acc <- cur o acc
+        double M[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                M[3 * r + q] = cur.M[3 * r] * acc.M[q] + cur.M[3 * r + 1] * acc.M[3 + q] + cur.M[3 * r + 2] * acc.M[6 + q];
+        affine_apply(cur, acc.b);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc.M[i] = M[i];
+    }
+    double* w = gwork + (size_t)g * kBsWork * ca.NT + tid;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) w[(size_t)i * ca.NT] = acc.M[i];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) w[(size_t)(9 + i) * ca.NT] = acc.b[i];
+}
+
+__global__ void __launch_bounds__(96) blender_smooth_carry_groups_kernel(const BsChunkArgs ca, double* gwork, int ngroups) {
     const int tid = blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= ca.NT) return;
     double s[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = ca.work[(size_t)(9 + i) * ca.NT + tid];   // end state of chunk 0
-    for (int chunk = 1; chunk < ca.nchunks; ++chunk) {
-        double* w = ca.work + (size_t)chunk * kBsWork * ca.NT + tid;
-        double M[9], b[12];
-#pragma unroll
-        for (int i = 0; i < 9; ++i) M[i] = w[(size_t)i * ca.NT];
-#pragma unroll
-        for (int i = 0; i < 12; ++i) b[i] = w[(size_t)(9 + i) * ca.NT];
+    for (int i = 0; i < 12; ++i) s[i] = 0.0;   // arbitrary: chunk 0 has M = 0
+    Affine cur, nxt;
+    affine_load(nxt, gwork + tid, ca.NT);
+    for (int g = 0; g < ngroups; ++g) {
+        cur = nxt;
+        if (g + 1 < ngroups) affine_load(nxt, gwork + (size_t)(g + 1) * kBsWork * ca.NT + tid, ca.NT);
+        double* w = gwork + (size_t)g * kBsWork * ca.NT + tid;
 #pragma unroll
         for (int i = 0; i < 12; ++i) w[(size_t)(21 + i) * ca.NT] = s[i];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const double s0 = s[3 * i], s1 = s[3 * i + 1], s2 = s[3 * i + 2];
-            s[3 * i + 0] = b[3 * i + 0] + (M[0] * s0 + M[1] * s1 + M[2] * s2);
-            s[3 * i + 1] = b[3 * i + 1] + (M[3] * s0 + M[4] * s1 + M[5] * s2);
-            s[3 * i + 2] = b[3 * i + 2] + (M[6] * s0 + M[7] * s1 + M[8] * s2);
-        }
+        affine_apply(cur, s);
     }
     double* st = ca.s.state + 2 + (size_t)tid * 12;
 #pragma unroll
@@ -502,6 +551,26 @@ __global__ void __launch_bounds__(96) blender_smooth_carry_kernel(const BsChunkA
         st[i] = s[3 * i];
         st[4 + i] = s[3 * i + 1];
         st[8 + i] = s[3 * i + 2];
+    }
+}
+
+__global__ void __launch_bounds__(96) blender_smooth_carry_chunks_kernel(const BsChunkArgs ca, const double* gwork, int ngroups) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = gtid / ca.NT, tid = gtid % ca.NT;
+    if (g >= ngroups) return;
+    const int c0 = g * kBsGroup, c1 = min(ca.nchunks, c0 + kBsGroup);
+    double s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = gwork[((size_t)g * kBsWork + 21 + i) * ca.NT + tid];
+    Affine cur, nxt;
+    affine_load(nxt, ca.work + (size_t)c0 * kBsWork * ca.NT + tid, ca.NT);
+    for (int c = c0; c < c1; ++c) {
+        cur = nxt;
+        if (c + 1 < c1) affine_load(nxt, ca.work + (size_t)(c + 1) * kBsWork * ca.NT + tid, ca.NT);
+        double* w = ca.work + (size_t)c * kBsWork * ca.NT + tid;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) w[(size_t)(21 + i) * ca.NT] = s[i];
+        affine_apply(cur, s);
     }
 }
 
@@ -638,18 +707,24 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
             if (s->d_work) cudaFree(s->d_work);
             s->d_work = nullptr;
             s->work_chunks = 0;
-            CUDA_TRY(h, cudaMalloc(&s->d_work, (size_t)ca.nchunks * kBsWork * threads * sizeof(double)));
+            const size_t maps = (size_t)ca.nchunks + (ca.nchunks + kBsGroup - 1) / kBsGroup;   // chunks, then groups
+            CUDA_TRY(h, cudaMalloc(&s->d_work, maps * kBsWork * threads * sizeof(double)));
             s->work_chunks = (size_t)ca.nchunks;
         }
         ca.work = s->d_work;
         const long long ta = (long long)ca.nchunks * threads, tc = (long long)(ca.nchunks - 1) * threads;
         if (f64) blender_smooth_chunk_kernel<double4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
         else blender_smooth_chunk_kernel<float4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
-        blender_smooth_carry_kernel<<<(threads + 95) / 96, 96, 0, st>>>(ca);
+        const int ngroups = (ca.nchunks + kBsGroup - 1) / kBsGroup;
+        double* gwork = s->d_work + (size_t)ca.nchunks * kBsWork * threads;
+        const unsigned gblocks = (unsigned)(((long long)ngroups * threads + 95) / 96);
+        blender_smooth_carry_compose_kernel<<<gblocks, 96, 0, st>>>(ca, gwork, ngroups);
+        blender_smooth_carry_groups_kernel<<<(threads + 95) / 96, 96, 0, st>>>(ca, gwork, ngroups);
+        blender_smooth_carry_chunks_kernel<<<gblocks, 96, 0, st>>>(ca, gwork, ngroups);
         if (f64) blender_smooth_chunk_kernel<double4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
         else blender_smooth_chunk_kernel<float4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
         CUDA_TRY(h, cudaGetLastError());
-        h->launches += 3;
+        h->launches += 5;
     }
     blender_smooth_finish_kernel<<<1, 32, 0, st>>>(s->d_state, d_nout, F, Pout, s->P);
     CUDA_TRY(h, cudaGetLastError());

@@ -300,14 +300,14 @@ def test_batch_clip_matches_reference_golden(torch_cuda, dtype, tol, split):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("chunked,batches", [(True, [600]), (False, [600]), (True, [290, 310]), (True, [1, 599]),
-                                             (True, [300, 40, 260])])
+                                             (True, [300, 40, 260]), (True, [9000]), (True, [4500, 4500])])
 def test_batch_smooth_long_clip_vs_oracle(torch_cuda, chunked, batches):
-    """600 frames, person count changing, random invalid control points, non-zero r; the chunk-parallel path
-    (batches of more than 256 frames), the sequential kernel, and a clip streamed through both."""
+    """Person count changing, random invalid control points, non-zero r; the chunk-parallel path (batches of more
+    than 256 frames; 9000 frames = 71 chunks in 3 groups), the sequential kernel, and a clip streamed through both."""
     torch = torch_cuda
     from snowmocap_b200.blender import BlenderSmoothState
     rng = np.random.default_rng(77)
-    F, P = 600, 3
+    F, P = sum(batches), 3
     fzr = np.stack([rng.uniform(1.0, 3.0, 24), rng.uniform(0.5, 1.0, 24), rng.uniform(0.0, 0.5, 24)], axis=1)
     ctrl = np.cumsum(rng.normal(0, 0.01, (F, P, 24, 4)), axis=0) + rng.uniform(-2, 2, (1, P, 24, 4))
     ctrl[:, :, [k for k in range(24) if k != 1], 3] = 0.0
