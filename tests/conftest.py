@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not p.endswith("floor_rig.npz") and not os.path.basename(p).startswith(("smooth_", "blender_")))
+                  if not p.endswith("floor_rig.npz") and not os.path.basename(p).startswith(("smooth_", "blender_", "pipeline_")))
 
 
 def smooth_golden_names():

@@ -11,6 +11,10 @@ Run in the build container only:
                         ``Human_Triangulation_Blender_Smooth`` + ``Human_Triangulation_To_Blender_Result``
                         (main.py:80-87) with the shipped ``configs/blender_smooth_profile.json``; person counts
                         vary and some control points are invalid on some frames (also on the first).
+``pipeline_main.npz``   the whole per-frame body of the reference's ``main.py`` (:50-87) on 10 synthetic frames of
+                        the shipped 4-camera calibration with the shipped thresholds: add_human_2D_points ->
+                        Human_Triangulation -> Condense -> Smooth -> Blender -> Blender_Smooth ->
+                        To_Blender_Result; inputs (float32 2D keypoints) and the final per-frame control points.
 ``blender_profiles.npz`` the two shipped profiles (names in order; f, z, r per control point).
 Positions are stored as (x, y, z, 0), ``root_rotation`` as (w, x, y, z) -- the layout of the CUDA path.
 """
@@ -25,7 +29,11 @@ REF = os.environ.get("SNOW_REFERENCE", "/root/reference")
 sys.path.insert(0, REF)
 sys.dont_write_bytecode = True
 
-import snowvision.blender as refb  # noqa: E402  (the real reference)
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import snowvision as ref  # noqa: E402  (the real reference)
+import snowvision.blender as refb  # noqa: E402
+from snowmocap_b200 import synth  # noqa: E402
 
 with open(os.path.join(REF, "configs", "blender_armature_profile.json")) as fh:
     ARMATURE = json.load(fh)
@@ -102,5 +110,52 @@ def main():
     print("blender_smooth: frames", F, "persons out", [d[f"ctrl_{t}"].shape[0] for t in range(F)])
 
 
+def pipeline():
+    """main.py:50-87 of the reference, frame after frame."""
+    with open(os.path.join(REF, "configs", "snowmocap_default_config.json")) as fh:
+        cfg = json.load(fh)
+    z = np.load(os.path.join(HERE, "floor_rig.npz"))
+    rig = synth.Rig(z["K"], z["R"], z["t"])
+    F = 10
+    data = synth.make_frames(rig, F, 1, 133, seed=41)
+    group = ref.CameraGroup(cap_ids=list(range(rig.C)), resolutions=[(1280, 720)] * rig.C)
+    for c in range(rig.C):
+        group.cameras[c].K, group.cameras[c].R = rig.K[c].copy(), rig.R[c].copy()
+        group.cameras[c].t = rig.t[c].reshape(3, 1).copy()
+    kst = 0.5   # the shipped file says 3.0, which rejects every rtmlib score <= 1; SURVEY 8d uses 0.5
+    prev_tri, prev_bl, d = None, None, {}
+    for f in range(F):
+        for c in range(rig.C):
+            group.add_human_2D_points(data["kpts"][f, c, 0].astype(np.float64), data["scores"][f, c, 0].astype(np.float64), c)
+        with np.errstate(all="ignore"):
+            tri = ref.Human_Triangulation(group, keypoint_score_threshold=kst,
+                                          average_score_threshold=cfg["average_score_threshold"],
+                                          distance_threshold=cfg["distance_threshold"])
+            tri = ref.Human_Triangulation_Condense(tri, condense_distance_tol=cfg["condense_distance_tol"],
+                                                   condense_person_num_tol=cfg["condense_person_num_tol"],
+                                                   condense_score_tol=cfg["condense_score_tol"],
+                                                   center_point_index=cfg["center_point_index"],
+                                                   keypoint_num=cfg["keypoint_num"])
+            tri = ref.Human_Triangulation_Smooth(tri, prev_tri, f=cfg["smooth_f"], z=cfg["smooth_z"], r=cfg["smooth_r"],
+                                                 delta_time=cfg["smooth_delta_time"])
+            prev_tri = tri
+            bl = refb.Human_Triangulation_Blender(tri, ARMATURE)
+            bl = refb.Human_Triangulation_Blender_Smooth(bl, ARMATURE, SMOOTH, prev_bl, delta_time=cfg["smooth_delta_time"])
+            prev_bl = bl
+            fin = refb.Human_Triangulation_To_Blender_Result(bl)
+        group.clear_2D_points()
+        d[f"ctrl_{f}"], d[f"valid_{f}"] = pack(fin["armature"], fin["score"])
+        d[f"joints_{f}"] = np.array(tri["hrnet_triangulate_points"], np.float64).reshape(-1, 133, 3)
+    params = dict(kst=kst, ast=cfg["average_score_threshold"], dthr=cfg["distance_threshold"],
+                  cond_tol=cfg["condense_distance_tol"], num_tol=cfg["condense_person_num_tol"],
+                  score_tol=cfg["condense_score_tol"], center=cfg["center_point_index"], keypoint_num=cfg["keypoint_num"],
+                  smooth_f=cfg["smooth_f"], smooth_z=cfg["smooth_z"], smooth_r=cfg["smooth_r"],
+                  smooth_delta_time=cfg["smooth_delta_time"])
+    np.savez_compressed(os.path.join(HERE, "pipeline_main.npz"), kpts=data["kpts"], scores=data["scores"],
+                        params=json.dumps(params), **d)
+    print("pipeline_main: frames", F, "persons", [d[f"ctrl_{f}"].shape[0] for f in range(F)])
+
+
 if __name__ == "__main__":
+    pipeline()
     main()

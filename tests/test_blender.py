@@ -361,3 +361,88 @@ def test_pipeline_run_to_control_points(torch_cuda):
     got = ctrl.cpu().numpy().reshape(-1, 24, 4)
     assert rel_l2(got[want_valid], want[want_valid]) < TOL_F32
     eng.close()
+
+
+# ---- the whole per-frame body of the reference's main.py (:50-87) ----------------------------------------------
+def _pipeline_golden():
+    g = _golden("pipeline_main")
+    return g, json.loads(str(g["params"]))
+
+
+@pytest.mark.gpu
+def test_main_py_sequence_through_dropin_names(torch_cuda):
+    """main.py:50-87 with only the import changed: add_human_2D_points -> Human_Triangulation -> Condense -> Smooth
+    -> Blender -> Blender_Smooth -> To_Blender_Result, frame after frame, against the real reference's output."""
+    import snowmocap_b200 as sv
+    from conftest import floor_rig
+    g, p = _pipeline_golden()
+    names, fzr = _profiles()
+    armature = {n: [] for n in names}
+    smooth = {n: fzr[k].tolist() for k, n in enumerate(names)}
+    rig = floor_rig()
+    group = sv.CameraGroup(cap_ids=list(range(rig.C)), resolutions=[(1280, 720)] * rig.C)
+    for c in range(rig.C):
+        group.cameras[c].K, group.cameras[c].R, group.cameras[c].t = rig.K[c], rig.R[c], rig.t[c].reshape(3, 1)
+    prev_tri, prev_bl = None, None
+    F = g["kpts"].shape[0]
+    for f in range(F):
+        for c in range(rig.C):
+            group.add_human_2D_points(g["kpts"][f, c, 0], g["scores"][f, c, 0], c)
+        tri = sv.Human_Triangulation(group, keypoint_score_threshold=p["kst"], average_score_threshold=p["ast"],
+                                     distance_threshold=p["dthr"])
+        tri = sv.Human_Triangulation_Condense(tri, condense_distance_tol=p["cond_tol"],
+                                              condense_person_num_tol=p["num_tol"], condense_score_tol=p["score_tol"],
+                                              center_point_index=p["center"], keypoint_num=p["keypoint_num"])
+        tri = sv.Human_Triangulation_Smooth(tri, prev_tri, f=p["smooth_f"], z=p["smooth_z"], r=p["smooth_r"],
+                                            delta_time=p["smooth_delta_time"])
+        prev_tri = tri
+        bl = sv.Human_Triangulation_Blender(tri, armature)
+        bl = sv.Human_Triangulation_Blender_Smooth(bl, armature, smooth, prev_bl, delta_time=p["smooth_delta_time"])
+        prev_bl = bl
+        fin = sv.Human_Triangulation_To_Blender_Result(bl)
+        group.clear_2D_points()
+        want, want_valid = g[f"ctrl_{f}"], g[f"valid_{f}"]
+        assert rel_l2(np.array(tri["hrnet_triangulate_points"]).reshape(-1, 133, 3), g[f"joints_{f}"]) < 1e-9
+        assert len(fin["armature"]) == len(fin["score"]) == want.shape[0] == 1
+        got = np.zeros((24, 4))
+        for k, name in enumerate(names):
+            v = np.asarray(fin["armature"][0][name])
+            got[k, :v.shape[0]] = v
+            assert fin["score"][0][name] == int(want_valid[0, k]) == 1
+        assert rel_l2(got, want[0]) < 1e-9, f
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("f64", 1e-6), ("f32", 1e-4)])
+def test_main_py_sequence_device_resident_batch(torch_cuda, precision, tol):
+    """The same clip as one batch that never leaves the device: snowtri_run -> snowtri_smooth_run ->
+    snowtri_blender_run -> snowtri_blender_smooth_run, against the real reference's final control points
+    (north_star bound 1e-4 in float32 arithmetic; float64 arithmetic with float32 storage 1e-6)."""
+    torch = torch_cuda
+    from conftest import floor_rig
+    from snowmocap_b200.blender import BlenderControl, BlenderSmoothState
+    from snowmocap_b200.engine import SmoothState, TriangulationEngine
+    g, p = _pipeline_golden()
+    _, fzr = _profiles()
+    rig = floor_rig()
+    eng = TriangulationEngine(rig.K, rig.R, rig.t, device=0, precision=precision, kst=p["kst"], ast=p["ast"],
+                              dthr=p["dthr"], cond_tol=p["cond_tol"], num_tol=p["num_tol"], score_tol=p["score_tol"],
+                              center=p["center"])
+    kp, sc = torch.from_numpy(g["kpts"]).cuda(), torch.from_numpy(g["scores"]).cuda()
+    res = eng.run(kp, sc, None, Pout=1, keypoint_num=p["keypoint_num"])
+    out, nout = res["out"], res["nout"]
+    sm = SmoothState(eng, 1, 133, p["smooth_f"], p["smooth_z"], p["smooth_r"])
+    nsm = sm.run(out, nout, p["smooth_delta_time"])
+    ctrl, valid = BlenderControl(eng).run(out, nsm)
+    bs = BlenderSmoothState(eng, 1, fzr)
+    nfin = bs.run(ctrl, valid, nsm, p["smooth_delta_time"])
+    torch.cuda.synchronize()
+    F = g["kpts"].shape[0]
+    assert (nfin.cpu().numpy() == 1).all()
+    got = ctrl.cpu().numpy()[:, 0]
+    want = np.stack([g[f"ctrl_{f}"][0] for f in range(F)])
+    joints = np.stack([g[f"joints_{f}"][0] for f in range(F)])
+    assert rel_l2(out.cpu().numpy()[:, 0, :, :3], joints) < tol
+    assert rel_l2(got, want) < tol
+    assert (valid.cpu().numpy() == (1 << 24) - 1).all()
+    sm.close(); bs.close(); eng.close()
