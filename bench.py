@@ -198,6 +198,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other precision modes")
     ap.add_argument("--jit", default="auto", choices=["off", "auto", "always"],
                     help="rig-specialised single-person kernel compiled at run time (NVRTC)")
@@ -219,8 +220,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if not args.no_numa:
+            from snowmocap_b200.dist import bind_host_to_gpu
+            numa_cpus = bind_host_to_gpu(local)     # before the pinned buffers of the e2e leg are allocated
 
     rig_kind, C, P, J, F, pk, pout, desc = WORKLOADS[wl]
     F = args.frames or F
@@ -344,7 +349,8 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": kp_per_step * esteps / float(dt.item()), "unit": "keypoints/s",
                "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(sum(v.nbytes for v in ho.values())),
-               "steps": esteps, "api": "snowtri_run_host (C ABI, pinned host buffers)"}
+               "steps": esteps, "api": "snowtri_run_host (C ABI, pinned host buffers)",
+               "host_cores_bound_to_gpu_numa_node": numa_cpus}
 
     # ---- final all-gather of the 3D joints (timed once, not part of a step) ---------------------
     gather = None

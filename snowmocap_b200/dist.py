@@ -40,3 +40,30 @@ def triangulate_sharded(engine, kpts_local, scores_local, counts_local, F, Pout=
     if not gather or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return res
     return {k: all_gather_frames(v, F, group) for k, v in res.items()}
+
+
+def bind_host_to_gpu(device_index):
+    """Pin this process to the CPU cores closest to its GPU (NVML's ideal affinity) so the pinned host buffers it
+    allocates afterwards are first-touched on the GPU's NUMA node -- with one process per GPU this keeps every
+    rank's host<->device copies off the inter-socket link.  Returns the number of cores bound, or 0 if NVML or the
+    affinity call is unavailable (the caller carries on unbound)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device_index)
+        if hasattr(props, "uuid"):
+            handle = pynvml.nvmlDeviceGetHandleByUUID(f"GPU-{props.uuid}")
+        else:
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(
+                f"{getattr(props, 'pci_domain_id', 0):08x}:{props.pci_bus_id:02x}:{getattr(props, 'pci_device_id', 0):02x}.0")
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
