@@ -365,7 +365,26 @@ def main():
         torch.cuda.synchronize()
         gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         dist.all_reduce(gms, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(gms.item()), "bytes_received_per_gpu": int(full.numel() * 4 * (world - 1) // world)}
+        gather = {"ms": float(gms.item()), "bytes_received_per_gpu": int(full.numel() * 4 * (world - 1) // world),
+                  "api": "torch.distributed.all_gather_into_tensor (NCCL)"}
+        # the same gather through the C ABI (snowtri_allgather on a communicator owned by the handle), checked
+        # against the torch.distributed result
+        try:
+            from snowmocap_b200.dist import all_gather_frames_native, init_native_comm
+            init_native_comm(eng)
+            all_gather_frames_native(eng, out["out"], world)
+            barrier()
+            g0.record()
+            full2 = all_gather_frames_native(eng, out["out"], world)
+            g1.record()
+            torch.cuda.synchronize()
+            gms = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(gms, op=dist.ReduceOp.MAX)
+            gather["c_abi"] = {"ms": float(gms.item()), "api": "snowtri_allgather (ncclAllGather, handle-owned communicator)",
+                               "equal_to_torch": bool(torch.equal(full2, full))}
+            del full2
+        except Exception as e:   # reported, not fatal: the gather is not part of a step
+            gather["c_abi"] = {"error": str(e)[:200]}
         del full
 
     if rank == 0:

@@ -25,6 +25,8 @@
 #ifndef SNOWTRI_H_
 #define SNOWTRI_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -209,6 +211,21 @@ int snowtri_blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, float*
 int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smooth_t* s, double* d_ctrl, const unsigned* d_valid,
                                    const int* d_nout, int* d_nsmooth, int F, int Pout, double delta_time,
                                    void* stream);
+
+/* Final all-gather of the 3D joints across the GPUs of one box (north_star: frames shard across the GPUs, "NCCL
+ * over NVLink appears only as a final all-gather of 3D joints").  One process per GPU, one handle per process.
+ * NCCL ("libnccl.so.2") is loaded with dlopen at first use.  Either pass the host's own ncclComm_t, or let the handle
+ * own one: rank 0 fills 128 bytes with snowtri_comm_unique_id, the host ships them to every rank, every rank calls
+ * snowtri_comm_init(h, id, nranks, rank) (collective).
+ *   d_send  this rank's block (bytes_per_rank bytes, e.g. its (F/N, Pout, J, 4) float32 output)
+ *   d_recv  nranks * bytes_per_rank bytes, rank r's block at offset r * bytes_per_rank (frame order when ranks own
+ *           consecutive frame blocks of equal size)
+ * Asynchronous on `stream`. */
+int snowtri_comm_unique_id(void* id128);
+int snowtri_comm_init(snowtri_t* h, const void* id128, int nranks, int rank);
+int snowtri_comm_destroy(snowtri_t* h);
+int snowtri_allgather(snowtri_t* h, const void* d_send, void* d_recv, size_t bytes_per_rank, void* nccl_comm_or_null,
+                      void* stream);
 
 /* Introspection. */
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */

@@ -42,6 +42,10 @@ SYMBOLS = {
     "snowtri_blender_smooth_set_chunked": (_I, [_P, _I]),
     "snowtri_blender_smooth_run": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "snowtri_blender_smooth_run_f64": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
+    "snowtri_comm_unique_id": (_I, [_P]),
+    "snowtri_comm_init": (_I, [_P, _P, _I, _I]),
+    "snowtri_comm_destroy": (_I, [_P]),
+    "snowtri_allgather": (_I, [_P, _P, _P, ct.c_size_t, _P, _P]),
     "snowtri_last_error": (ct.c_char_p, [_P]),
     "snowtri_launch_count": (ct.c_longlong, [_P]),
     "snowtri_last_launch_info": (_I, [_P, ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I), ct.POINTER(_I)]),

@@ -14,7 +14,7 @@ OBJ_DIR = os.path.join(PKG, "build")
 SOURCES = [os.path.join(CSRC, "snowtri_capi.cu"), os.path.join(CSRC, "snowtri_p1.cu"),
            os.path.join(CSRC, "snowtri_smooth.cu"), os.path.join(CSRC, "snowtri_general.cu"),
            os.path.join(CSRC, "snowtri_jit.cu"), os.path.join(CSRC, "snowtri_dlt.cu"),
-           os.path.join(CSRC, "snowtri_blender.cu")]
+           os.path.join(CSRC, "snowtri_blender.cu"), os.path.join(CSRC, "snowtri_comm.cu")]
 
 
 def _headers():

@@ -104,6 +104,7 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
         if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->gen_scratch) cudaFree(h->gen_scratch);
     snowtri_jit_free(h);
+    snowtri_comm_destroy(h);
     free(h->p1_args);
     if (h->pipe_in) {
         cudaStreamDestroy(h->pipe_in);

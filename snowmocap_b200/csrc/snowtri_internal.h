@@ -44,6 +44,8 @@ struct snowtri_handle {
     int jit_mode;             // 0 off, 1 auto (long batches), 2 always
     void* jit_cache;          // rig-specialised kernels (snowtri_jit.cu)
     char jit_status[512];
+    void* nccl_comm;          // communicator owned by the handle (snowtri_comm.cu), or NULL
+    int nccl_nranks, nccl_rank;
     int allow_f32_multi;  // tests only: float32 general kernel with several persons per camera
     size_t stage_cap[6];
     char err[512];

@@ -67,3 +67,34 @@ def bind_host_to_gpu(device_index):
         return len(cpus)
     except Exception:
         return 0
+
+
+def init_native_comm(engine, group=None):
+    """Give ``engine``'s handle its own NCCL communicator over the ranks of ``group`` (collective): rank 0 draws the
+    unique id through the C ABI (``snowtri_comm_unique_id``), torch.distributed ships the 128 bytes,
+    every rank calls ``snowtri_comm_init``."""
+    import ctypes as ct
+    from . import _lib
+    lib = _lib.load()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    buf = ct.create_string_buffer(128)
+    if rank == 0:
+        _lib.check(lib.snowtri_comm_unique_id(buf))
+    box = [bytes(buf.raw)]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    ident = ct.create_string_buffer(box[0], 128)
+    with torch.cuda.device(engine.device):
+        _lib.check(lib.snowtri_comm_init(engine._h, ident, world, rank), engine._h)
+
+
+def all_gather_frames_native(engine, local, world, stream=None):
+    """``snowtri_allgather`` of equal-sized per-rank frame blocks (F/world frames each) through the handle's own
+    communicator (``init_native_comm`` first): returns the (F, ...) tensor, rank r's frames at block r."""
+    from . import _lib
+    local = local.contiguous()
+    out = torch.empty((local.shape[0] * world,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    st = torch.cuda.current_stream(local.device).cuda_stream if stream is None else stream
+    with torch.cuda.device(engine.device):
+        _lib.check(engine._lib.snowtri_allgather(engine._h, local.data_ptr(), out.data_ptr(),
+                                                 local.numel() * local.element_size(), None, st), engine._h)
+    return out

@@ -775,3 +775,30 @@ def test_random_configurations_vs_c_oracle(torch_cuda, seed):
             assert np.array_equal(out[valid][:, :, 3] == 0, ref["kscores"][valid] == 0), tag
             tol = TOL_FUSED if precision == "f64" else TOL_NORTH_STAR
             assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol, tag
+
+
+# ---- final all-gather through the C ABI -----------------------------------------------------------
+def test_native_allgather_single_rank(torch_cuda):
+    """snowtri_comm_unique_id / snowtri_comm_init / snowtri_allgather with a one-rank communicator (the round-end GPU
+    box has one GPU; tools/allgather_check.py is the 2-rank check)."""
+    torch = torch_cuda
+    import ctypes as ct
+    from snowmocap_b200 import _lib
+    rig = floor_rig()
+    eng = _engine(rig, synth.DEFAULT_PARAMS)
+    lib = eng._lib
+    ident = ct.create_string_buffer(128)
+    _lib.check(lib.snowtri_comm_unique_id(ident))
+    assert any(ident.raw)
+    x = torch.arange(4096, dtype=torch.float32, device="cuda")
+    y = torch.zeros_like(x)
+    rc = lib.snowtri_allgather(eng._h, x.data_ptr(), y.data_ptr(), x.numel() * 4, None, None)
+    assert rc == _lib.E_ARG, "no communicator yet"
+    _lib.check(lib.snowtri_comm_init(eng._h, ident, 1, 0), eng._h)
+    assert lib.snowtri_comm_init(eng._h, ident, 1, 0) == _lib.E_ARG, "a handle owns at most one communicator"
+    _lib.check(lib.snowtri_allgather(eng._h, x.data_ptr(), y.data_ptr(), x.numel() * 4, None,
+                                     torch.cuda.current_stream().cuda_stream), eng._h)
+    torch.cuda.synchronize()
+    assert torch.equal(x, y)
+    assert lib.snowtri_comm_destroy(eng._h) == _lib.OK
+    eng.close()
