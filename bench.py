@@ -181,6 +181,47 @@ def _emit(line):
 _REAL_STDOUT = 1
 
 
+def time_downstream(torch, eng, out, pout, J, reps=5):
+    """Device-resident continuation of the step's output through the remaining per-frame stages of the reference's
+    main.py (:72-87): Human_Triangulation_Smooth, Human_Triangulation_Blender, Human_Triangulation_Blender_Smooth.
+    Times in ms per batch (CUDA events, mean of ``reps`` after one warm-up)."""
+    from snowmocap_b200.blender import BlenderControl, BlenderSmoothState
+    from snowmocap_b200.engine import SmoothState
+    pts, nout = out["out"].clone(), out["nout"]
+    F = pts.shape[0]
+    sm = SmoothState(eng, pout, J, 2.5, 0.75, 0.0)          # configs/snowmocap_default_config.json:18-21
+    bc = BlenderControl(eng)
+    bs = BlenderSmoothState(eng, pout, [[2.5, 0.75, 0.0]] * 24)
+    ctrl, valid = bc.run(pts, nout)
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def smooth():
+        sm.reset()
+        sm.run(pts, nout, 1 / 30)
+
+    def bsmooth():
+        bs.reset()
+        bs.run(ctrl, valid, nout, 1 / 30)
+
+    res = {"frames": int(F), "persons_per_frame_slots": int(pout),
+           "snowtri_smooth_run_ms": timed(smooth),
+           "snowtri_blender_run_ms": timed(lambda: bc.run(pts, nout)),
+           "snowtri_blender_smooth_run_ms": timed(bsmooth)}
+    sm.close()
+    bs.close()
+    return res
+
+
 def main():
     global _REAL_STDOUT
     # NCCL / torchrun print banners on stdout; the driver wants exactly one JSON line there
@@ -387,6 +428,14 @@ def main():
             gather["c_abi"] = {"error": str(e)[:200]}
         del full
 
+    # ---- the rest of main.py's per-frame body on the same batch, device-resident (not part of a step) ---------
+    downstream = None
+    if rank == 0 and world == 1 and J >= 130 and not args.no_others:
+        try:
+            downstream = time_downstream(torch, eng, out, pout, J)
+        except Exception as e:   # reported, not fatal
+            downstream = {"error": str(e)[:200]}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         alg_bytes = (12 * C + 16) * P * J * F                     # per output keypoint, per launch
@@ -418,7 +467,7 @@ def main():
                              "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
                              "frac_of_8TBs_spec": achieved / 8000.0,
                              "pair_solves_per_sec": solves / (kernel_ms * 1e-3)},
-                "other_precisions": others, "allgather": gather}
+                "other_precisions": others, "allgather": gather, "downstream": downstream}
         if not args.no_cpu and world == 1:      # CPU baseline legs: rank 0 at N=1 only
             cores = os.cpu_count() or 1
             per_core = loop_frames_per_core(C, P, J)

@@ -446,3 +446,37 @@ def test_main_py_sequence_device_resident_batch(torch_cuda, precision, tol):
     assert rel_l2(got, want) < tol
     assert (valid.cpu().numpy() == (1 << 24) - 1).all()
     sm.close(); bs.close(); eng.close()
+
+
+@pytest.mark.gpu
+def test_control_points_full_size_properties(torch_cuda):
+    """BASELINE cfg2 size (131 072 frames x 1 person): translation equivariance (positions move with the person,
+    the root quaternion does not change at all), determinism, and a random sample of rows against the oracle."""
+    torch = torch_cuda
+    from snowmocap_b200.blender import BlenderControl
+    eng = _util_engine()
+    F = 131072
+    g = torch.Generator(device="cuda").manual_seed(11)
+    # coordinates on a 1/1024 grid in [0, 4): adding an integer offset is exact in float32
+    pts = torch.randint(0, 4096, (F, 1, 133, 4), generator=g, device="cuda").to(torch.float32) / 1024.0
+    bc = BlenderControl(eng)
+    ctrl, valid = bc.run(pts, None)
+    ctrl2, valid2 = bc.run(pts, None)
+    assert torch.equal(ctrl, ctrl2) and torch.equal(valid, valid2)
+    off = torch.tensor([3.0, -2.0, 1.0, 0.0], device="cuda")
+    ctrl_s, valid_s = bc.run(pts + off, None)
+    torch.cuda.synchronize()
+    assert torch.equal(valid, valid_s)
+    full = (valid == (1 << 24) - 1).view(-1)
+    assert full.float().mean() > 0.99
+    q, q_s = ctrl[:, 0, 1][full], ctrl_s[:, 0, 1][full]
+    assert torch.equal(q, q_s), "differences of exactly shifted inputs are identical"
+    assert torch.allclose(q.double().norm(dim=1), torch.ones(1, dtype=torch.float64, device="cuda"), atol=1e-6)
+    pos = [k for k in range(24) if k != 1]
+    d = (ctrl_s[:, 0, pos] - ctrl[:, 0, pos])[full]
+    assert (d - off).abs().max().item() < 2e-6
+    rows = np.random.default_rng(0).choice(F, 200, replace=False)
+    want, want_valid = bo.control_points_batch(pts[rows, 0, :, :3].cpu().numpy().astype(np.float64))
+    got = ctrl[rows, 0].cpu().numpy()
+    assert np.array_equal(_masks(valid[rows, 0].cpu().numpy()), want_valid)
+    assert rel_l2(got[want_valid], want[want_valid]) < TOL_F32
