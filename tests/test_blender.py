@@ -76,6 +76,41 @@ def test_oracle_smooth_matches_reference_golden():
         np.testing.assert_allclose(np.nan_to_num(y), np.nan_to_num(want), rtol=0, atol=1e-13)
 
 
+# ---- CPU: host logic of the drop-in names (no device is touched on these paths) --------------------------------
+def test_dropin_host_checks_run_before_the_device_is_needed():
+    from snowmocap_b200 import Human_Triangulation_Blender, Human_Triangulation_To_Blender_Result
+    names, _ = _profiles()
+    profile = {n: [] for n in names}
+    empty = {"hrnet_triangulate_points": [], "hrnet_triangulate_keypoint_scores": []}
+    assert Human_Triangulation_Blender(empty, profile) == {"blender_armature_control_points": [],
+                                                          "blender_armature_control_points_scores": []}
+    short = {"hrnet_triangulate_points": [np.zeros((30, 3))], "hrnet_triangulate_keypoint_scores": [np.ones(30)]}
+    with pytest.raises(IndexError):          # the reference indexes person[129] (blender.py:103)
+        Human_Triangulation_Blender(short, profile)
+    whole = {"hrnet_triangulate_points": [np.zeros((133, 3))], "hrnet_triangulate_keypoint_scores": [np.ones(133)]}
+    with pytest.raises(NameError):           # the reference eval()s the profile's names (blender.py:133)
+        Human_Triangulation_Blender(whole, {"tail_ik": []})
+    # zip() truncation of To_Blender_Result (blender.py:183): scores of persons without a follower are dropped
+    res = Human_Triangulation_To_Blender_Result({"blender_armature_control_points": [{"a": [0, 0, 0]}],
+                                                 "blender_armature_control_points_scores": [{"a": 1}, {"a": 1}]})
+    assert res == {"armature": [{"a": [0, 0, 0]}], "score": [{"a": 1}]}
+
+
+def test_control_point_table_matches_oracle_and_header():
+    import re
+    from snowmocap_b200.blender import CONTROL_POINTS, _pack_control
+    assert CONTROL_POINTS == bo.CONTROL_POINTS
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "snowtri.h")).read()
+    listed = re.findall(r"(\d+) ([a-z_]+_(?:position|rotation|ik|pole))", header)
+    assert [n for _, n in sorted(((int(i), n) for i, n in listed))] == list(CONTROL_POINTS)
+    cps = [{"root_rotation": [1.0, 0.0, 0.0, 0.0], "head_ik": [1.0, 2.0, 3.0]}]
+    scs = [{"root_rotation": 1, "head_ik": 0}]
+    ctrl, valid = _pack_control(cps, scs, ["root_rotation", "head_ik"])
+    assert ctrl.shape == (1, 1, 24, 4) and valid.tolist() == [[1 << 1]]
+    assert ctrl[0, 0, 1].tolist() == [1.0, 0.0, 0.0, 0.0] and ctrl[0, 0, 22].tolist() == [1.0, 2.0, 3.0, 0.0]
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def torch_cuda():
