@@ -343,6 +343,10 @@ __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothA
 // Inside a chunk the arithmetic is the reference's recurrence; only the hand-over between chunks is evaluated
 // differently (agreement with the sequential kernel ~1e-15 relative).
 constexpr int kBsChunk = 128;
+#ifndef BS_BATCH_BYTES
+#define BS_BATCH_BYTES 256
+#endif
+constexpr int kBsBatchBytes = BS_BATCH_BYTES;   // input bytes a thread holds in registers per batch (16 float4 / 8 double4)
 constexpr int kBsWork = 33;   // per (chunk, thread): M (9), b (4 channels x 3), start (4 channels x 3)
 
 struct BsChunkArgs {
@@ -400,29 +404,26 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
         for (int i = 0; i < 4; ++i) xp[i] = y[i] = yd[i] = 0.0;
     }
     bool init = was_init || chunk > 0;
-    V buf[kBsAhead];
-    unsigned vb[kBsAhead];
-    int nb[kBsAhead];
+    // a batch of frames at a time: all loads issued back to back (clamped addresses), one wait, then the steps
+    constexpr int NB = kBsBatchBytes / (int)sizeof(V);
+    for (int t0 = t_begin; t0 < t_end; t0 += NB) {
+        V buf[NB];
+        unsigned vb[NB];
+        int nb[NB];
 #pragma unroll
-    for (int u = 0; u < kBsAhead; ++u)
-        if (t_begin + u < t_end) {
-            buf[u] = ctrl[(size_t)(t_begin + u) * stride + base];
-            vb[u] = a.valid[(size_t)(t_begin + u) * a.Pout + vbase];
-            nb[u] = a.nout[t_begin + u];
+        for (int u = 0; u < NB; ++u) {
+            const int t = min(t0 + u, t_end - 1);
+            buf[u] = ctrl[(size_t)t * stride + base];
+            vb[u] = a.valid[(size_t)t * a.Pout + vbase];
+            nb[u] = a.nout[t];
         }
-    for (int t0 = t_begin; t0 < t_end; t0 += kBsAhead) {
 #pragma unroll
-        for (int u = 0; u < kBsAhead; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const int t = t0 + u;
             if (t >= t_end) break;
             const V p = buf[u];
             const bool ok = (vb[u] >> c) & 1u;
             const int n = min(max(nb[u], 0), a.Pout);
-            if (t + kBsAhead < t_end) {
-                buf[u] = ctrl[(size_t)(t + kBsAhead) * stride + base];
-                vb[u] = a.valid[(size_t)(t + kBsAhead) * a.Pout + vbase];
-                nb[u] = a.nout[t + kBsAhead];
-            }
             const double x[4] = {(double)p.x, (double)p.y, (double)p.z, (double)p.w};
             if (!init) {   // only chunk 0 of a new clip: the seeding frame (blender.py:165-176)
                 init = true;

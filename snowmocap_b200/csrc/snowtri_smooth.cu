@@ -147,6 +147,10 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
 
 
 constexpr int kChunk = 128;  // frames per chunk of the parallel path
+#ifndef SMOOTH_BATCH_BYTES
+#define SMOOTH_BATCH_BYTES 256
+#endif
+constexpr int kSmoothBatchBytes = SMOOTH_BATCH_BYTES;  // input bytes a thread holds in registers per batch (16 float4 / 8 double4)
 
 // One frame of one (person, joint): the reference's update (triangulation.py:15-22) on the three axes.
 __device__ __forceinline__ void follower_step(const SmoothArgs& a, const double* x, double* xp, double* y, double* yd) {
@@ -197,25 +201,26 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
     const bool inrange = k < a.Pout;
     const size_t base = (size_t)(inrange ? k : 0) * a.J + j;
     int present = 0;
-    V buf[kSmoothAhead];
-    int nb[kSmoothAhead];
+    // Inputs are fetched a batch of frames at a time -- all loads of a batch issued back to back (clamped
+    // addresses, no branches), one wait, then the batch's recurrence steps from registers.  (A ring that refills one
+    // slot per step makes every step wait for the load it has just issued: a scoreboard wait covers every load
+    // assigned to it.)
+    constexpr int NB = kSmoothBatchBytes / (int)sizeof(V);
+    for (int t0 = t_begin; t0 < t_end; t0 += NB) {
+        V buf[NB];
+        int nb[NB];
 #pragma unroll
-    for (int u = 0; u < kSmoothAhead; ++u)
-        if (t_begin + u < t_end) {
-            buf[u] = pts[(size_t)(t_begin + u) * stride + base];
-            nb[u] = a.nout[t_begin + u];
+        for (int u = 0; u < NB; ++u) {
+            const int t = min(t0 + u, t_end - 1);
+            buf[u] = pts[(size_t)t * stride + base];
+            nb[u] = a.nout[t];
         }
-    for (int t0 = t_begin; t0 < t_end; t0 += kSmoothAhead) {
 #pragma unroll
-        for (int u = 0; u < kSmoothAhead; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const int t = t0 + u;
             if (t >= t_end) break;
             const V p = buf[u];
             const int n = min(max(nb[u], 0), a.Pout);
-            if (t + kSmoothAhead < t_end) {
-                buf[u] = pts[(size_t)(t + kSmoothAhead) * stride + base];
-                nb[u] = a.nout[t + kSmoothAhead];
-            }
             const double x[3] = {(double)p.x, (double)p.y, (double)p.z};
             if (!was_init && t == 0) {  // first frame of the clip: seed, pass through (reference :177-184)
                 if (k < n0) {
