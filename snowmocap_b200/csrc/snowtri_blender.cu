@@ -236,7 +236,10 @@ struct BlenderSmoothArgs {
     double k1[SNOWTRI_NCTRL], inv_k2[SNOWTRI_NCTRL], k3[SNOWTRI_NCTRL];
 };
 
-constexpr int kBsAhead = 4;
+#ifndef BS_BATCH_BYTES
+#define BS_BATCH_BYTES 256
+#endif
+constexpr int kBsBatchBytes = BS_BATCH_BYTES;   // input bytes a thread holds in registers per batch (16 float4 / 8 double4)
 
 template <typename V>
 __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothArgs a) {
@@ -260,29 +263,26 @@ __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothA
     const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
     const size_t base = (size_t)(inrange ? k : 0) * SNOWTRI_NCTRL + c;
     const size_t vbase = inrange ? k : 0;
-    V buf[kBsAhead];
-    unsigned vb[kBsAhead];
-    int nb[kBsAhead];
+    // inputs a batch of frames at a time: loads back to back (clamped addresses), one wait, then the steps
+    constexpr int NB = kBsBatchBytes / (int)sizeof(V);
+    for (int t0 = 0; t0 < a.F; t0 += NB) {
+        V buf[NB];
+        unsigned vb[NB];
+        int nb[NB];
 #pragma unroll
-    for (int u = 0; u < kBsAhead; ++u)
-        if (u < a.F) {
-            buf[u] = ctrl[(size_t)u * stride + base];
-            vb[u] = a.valid[(size_t)u * a.Pout + vbase];
-            nb[u] = a.nout[u];
+        for (int u = 0; u < NB; ++u) {
+            const int t = min(t0 + u, a.F - 1);
+            buf[u] = ctrl[(size_t)t * stride + base];
+            vb[u] = a.valid[(size_t)t * a.Pout + vbase];
+            nb[u] = a.nout[t];
         }
-    for (int t0 = 0; t0 < a.F; t0 += kBsAhead) {
 #pragma unroll
-        for (int u = 0; u < kBsAhead; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const int t = t0 + u;
             if (t >= a.F) break;
             const V p = buf[u];
             const bool ok = (vb[u] >> c) & 1u;
             const int n = min(max(nb[u], 0), a.Pout);
-            if (t + kBsAhead < a.F) {
-                buf[u] = ctrl[(size_t)(t + kBsAhead) * stride + base];
-                vb[u] = a.valid[(size_t)(t + kBsAhead) * a.Pout + vbase];
-                nb[u] = a.nout[t + kBsAhead];
-            }
             const double x[4] = {(double)p.x, (double)p.y, (double)p.z, (double)p.w};
             if (!init) {   // first frame of the clip (blender.py:165-176): followers start at the control point,
                 init = true;   // or at zero where it is invalid; the frame passes through
@@ -343,10 +343,6 @@ __global__ void __launch_bounds__(96) blender_smooth_kernel(const BlenderSmoothA
 // Inside a chunk the arithmetic is the reference's recurrence; only the hand-over between chunks is evaluated
 // differently (agreement with the sequential kernel ~1e-15 relative).
 constexpr int kBsChunk = 128;
-#ifndef BS_BATCH_BYTES
-#define BS_BATCH_BYTES 256
-#endif
-constexpr int kBsBatchBytes = BS_BATCH_BYTES;   // input bytes a thread holds in registers per batch (16 float4 / 8 double4)
 constexpr int kBsWork = 33;   // per (chunk, thread): M (9), b (4 channels x 3), start (4 channels x 3)
 
 struct BsChunkArgs {

@@ -56,7 +56,10 @@ struct SmoothArgs {
     double T, invT, k1, inv_k2, k3;
 };
 
-constexpr int kSmoothAhead = 4;  // frames of input prefetched ahead of the recurrence
+#ifndef SMOOTH_BATCH_BYTES
+#define SMOOTH_BATCH_BYTES 256
+#endif
+constexpr int kSmoothBatchBytes = SMOOTH_BATCH_BYTES;  // input bytes a thread holds in registers per batch (16 float4 / 8 double4)  -- measured 128: 0.247 ms, 256: 0.240 ms, 512: 0.265 ms per 131 072 frames
 
 template <typename V>  // float4 or double4
 __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
@@ -81,25 +84,23 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
     const size_t stride = (size_t)a.Pout * a.J;  // points per frame
     const bool inrange = k < a.Pout;
     const size_t base = (size_t)(inrange ? k : 0) * a.J + j;
-    V buf[kSmoothAhead];
-    int nb[kSmoothAhead];
+    // inputs a batch of frames at a time (see smooth_chunk_kernel): loads back to back, one wait, then the steps
+    constexpr int NB = kSmoothBatchBytes / (int)sizeof(V);
+    for (int t0 = 0; t0 < a.F; t0 += NB) {
+        V buf[NB];
+        int nb[NB];
 #pragma unroll
-    for (int u = 0; u < kSmoothAhead; ++u)
-        if (u < a.F) {
-            buf[u] = pts[(size_t)u * stride + base];
-            nb[u] = a.nout[u];
+        for (int u = 0; u < NB; ++u) {
+            const int t = min(t0 + u, a.F - 1);
+            buf[u] = pts[(size_t)t * stride + base];
+            nb[u] = a.nout[t];
         }
-    for (int t0 = 0; t0 < a.F; t0 += kSmoothAhead) {
 #pragma unroll
-        for (int u = 0; u < kSmoothAhead; ++u) {
+        for (int u = 0; u < NB; ++u) {
             const int t = t0 + u;
             if (t >= a.F) break;
             const V p = buf[u];
             const int n = min(max(nb[u], 0), a.Pout);
-            if (t + kSmoothAhead < a.F) {  // refill this slot for frame t + kSmoothAhead
-                buf[u] = pts[(size_t)(t + kSmoothAhead) * stride + base];
-                nb[u] = a.nout[t + kSmoothAhead];
-            }
             const double x[3] = {(double)p.x, (double)p.y, (double)p.z};
             if (!init) {  // first frame of the clip: seed the followers, points pass through (reference :177-184)
                 init = true;
@@ -147,10 +148,6 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
 
 
 constexpr int kChunk = 128;  // frames per chunk of the parallel path
-#ifndef SMOOTH_BATCH_BYTES
-#define SMOOTH_BATCH_BYTES 256
-#endif
-constexpr int kSmoothBatchBytes = SMOOTH_BATCH_BYTES;  // input bytes a thread holds in registers per batch (16 float4 / 8 double4)
 
 // One frame of one (person, joint): the reference's update (triangulation.py:15-22) on the three axes.
 __device__ __forceinline__ void follower_step(const SmoothArgs& a, const double* x, double* xp, double* y, double* yd) {
