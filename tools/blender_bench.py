@@ -8,11 +8,35 @@ Algorithmic bytes per person row: 28 joints x 12 B (x, y, z) read + 24 control p
 import json
 import os
 import sys
+import time
 
-import torch
+import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+
+
+def cpu_leg(seconds=10.0):
+    """The CPU restatement of Human_Triangulation_Blender (oracle/blender_oracle.py, one core, like the reference's
+    single-threaded per-frame call) on a bounded sample of the same synthetic rows."""
+    from oracle import blender_oracle as bo
+    rng = np.random.default_rng(7)
+    rows = (rng.random((512, 133, 3)) * 2.0).astype(np.float32).astype(np.float64)
+    n, t0 = 0, time.perf_counter()
+    with np.errstate(all="ignore"):
+        while time.perf_counter() - t0 < seconds:
+            bo.control_points(rows[n % 512])
+            n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "persons/s", "cores": 1, "kind": "port",
+            "sample": f"{n} person rows in {dt:.1f} s, NumPy restatement of blender.py:93-143 (oracle/blender_oracle.py)"}
+
+
+if "--cpu-only" in sys.argv:
+    print(json.dumps({"op": "Human_Triangulation_Blender (CPU)", "cpu_baseline": cpu_leg(), "host_cores": os.cpu_count()}))
+    sys.exit(0)
+
+import torch  # noqa: E402
 from snowmocap_b200.blender import BlenderControl, BlenderSmoothState  # noqa: E402
 from snowmocap_b200.triangulation import _util_engine  # noqa: E402
 
@@ -67,4 +91,5 @@ print(json.dumps({"op": "snowtri_blender_run", "F": F, "Pout": P, "J": J, "dtype
                   "algorithmic_GBs": gbs, "peak_GBs": peak, "frac_of_measured_hbm": gbs / peak,
                   "input_bytes": out.numel() * 4, "timing": "input larger than L2" if out.numel() * 4 > 126e6 else "input fits L2",
                   "nvcc_flags": os.environ.get("SNOWTRI_NVCC_FLAGS", ""),
+                  "cpu_baseline": None if os.environ.get("BLENDER_BENCH_NO_CPU") or os.environ.get("BLENDER_BENCH_NO_SMOOTH") else cpu_leg(),
                   "smooth": {"op": "snowtri_blender_smooth_run (reset + one batch of F frames)", **res_s}}))
