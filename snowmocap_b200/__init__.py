@@ -5,7 +5,7 @@ Drop-in names (reference ``snowvision.camera`` / ``snowvision.triangulation``):
 ``Human_Triangulation_Condense``, ``Human_Triangulation_Smooth``; from ``snowvision.blender``:
 ``Human_Triangulation_Blender``, ``Human_Triangulation_Blender_Smooth``, ``Human_Triangulation_To_Blender_Result``,
 ``save_blender_result``.  Batch API: ``TriangulationEngine``, ``triangulate_batch``, ``SmoothState``,
-``BlenderControl``, ``BlenderSmoothState``.
+``BlenderControl``, ``BlenderSmoothState``, ``clip_to_blender_result_list``.
 Importing the package does not need a GPU; calling into it does (no CPU fallback).
 """
 from .camera import Camera, CameraGroup  # noqa: F401
@@ -15,7 +15,7 @@ _LAZY = {"TriangulationEngine": "engine", "triangulate_batch": "engine", "Skew_R
          "Human_Triangulation_Smooth": "triangulation", "SmoothState": "engine",
          "Human_Triangulation_Blender": "blender", "Human_Triangulation_Blender_Smooth": "blender",
          "Human_Triangulation_To_Blender_Result": "blender", "save_blender_result": "blender",
-         "BlenderControl": "blender", "BlenderSmoothState": "blender"}
+         "BlenderControl": "blender", "BlenderSmoothState": "blender", "clip_to_blender_result_list": "blender"}
 
 
 __all__ = ["Camera", "CameraGroup"] + sorted(_LAZY)   # `from snowmocap_b200 import *` overrides the reference's names

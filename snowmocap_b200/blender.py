@@ -230,3 +230,23 @@ def Human_Triangulation_To_Blender_Result(result):
         blender_result["armature"].append(control_points)
         blender_result["score"].append(control_points_scores)
     return blender_result
+
+
+def clip_to_blender_result_list(ctrl, valid, nsmooth, blender_armature_profile):
+    """Batch counterpart of ``main.py:87``: the per-frame ``Human_Triangulation_To_Blender_Result`` dicts of a whole
+    clip from the arrays of ``BlenderControl.run`` / ``BlenderSmoothState.run`` -- ``ctrl`` (F,Pout,24,4), ``valid``
+    (F,Pout) bit masks, ``nsmooth`` (F,) persons per frame (tensors or arrays; copied to the host once).  The list can
+    be handed to ``save_blender_result`` and is what the reference appends frame after frame (blender.py:180-187)."""
+    _check_profile(blender_armature_profile)
+    ctrl = ctrl.detach().cpu().numpy() if isinstance(ctrl, torch.Tensor) else np.asarray(ctrl)
+    valid = valid.detach().cpu().numpy() if isinstance(valid, torch.Tensor) else np.asarray(valid)
+    nsmooth = nsmooth.detach().cpu().numpy() if isinstance(nsmooth, torch.Tensor) else np.asarray(nsmooth)
+    names = list(blender_armature_profile.keys())
+    frames = []
+    for f in range(ctrl.shape[0]):
+        armature, score = [], []
+        for k in range(min(int(nsmooth[f]), ctrl.shape[1])):
+            armature.append({n: ctrl[f, k, _INDEX[n], :_LEN[n]].astype(np.float64).tolist() for n in names})
+            score.append({n: int((int(valid[f, k]) >> _INDEX[n]) & 1) for n in names})
+        frames.append({"armature": armature, "score": score})
+    return frames

@@ -111,6 +111,39 @@ def test_control_point_table_matches_oracle_and_header():
     assert ctrl[0, 0, 1].tolist() == [1.0, 0.0, 0.0, 0.0] and ctrl[0, 0, 22].tolist() == [1.0, 2.0, 3.0, 0.0]
 
 
+def test_clip_to_blender_result_list_schema(tmp_path):
+    """Arrays of a clip -> the reference's per-frame {'armature': [...], 'score': [...]} list (blender.py:180-187)."""
+    from snowmocap_b200 import clip_to_blender_result_list, save_blender_result
+    g = _golden("blender_smooth")
+    names, _ = _profiles()
+    F = len(g["counts"])
+    ctrl = np.zeros((F, 3, 24, 4))
+    valid = np.zeros((F, 3), np.int32)
+    nsm = np.zeros(F, np.int32)
+    for t in range(F):
+        m = g[f"ctrl_{t}"].shape[0]
+        nsm[t] = m
+        ctrl[t, :m] = g[f"ctrl_{t}"]
+        valid[t, :m] = (g[f"valid_{t}"].astype(np.int64) << np.arange(24)).sum(-1)
+    frames = clip_to_blender_result_list(ctrl, valid, nsm, {n: [] for n in names})
+    assert len(frames) == F
+    for t in range(F):
+        assert set(frames[t]) == {"armature", "score"}
+        assert len(frames[t]["armature"]) == len(frames[t]["score"]) == nsm[t]
+        for k in range(nsm[t]):
+            assert list(frames[t]["armature"][k]) == names
+            for i, n in enumerate(names):
+                v = frames[t]["armature"][k][n]
+                assert len(v) == (4 if n == "root_rotation" else 3)
+                assert np.array_equal(np.asarray(v), g[f"ctrl_{t}"][k, i, :len(v)], equal_nan=True)
+                assert frames[t]["score"][k][n] == int(g[f"valid_{t}"][k, i])
+    path = tmp_path / "clip.json"
+    save_blender_result(frames, str(path))
+    assert len(json.loads(path.read_text())) == F
+    with pytest.raises(NameError):
+        clip_to_blender_result_list(ctrl, valid, nsm, {"tail_ik": []})
+
+
 # ---- GPU ----------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def torch_cuda():
