@@ -214,3 +214,16 @@ def test_sharded_gather_world2_gloo(F):
     for r in range(2):
         for k, v in want.items():
             assert np.array_equal(got[r][k], v.numpy()), (r, k)
+
+
+def test_bind_host_to_gpu_is_a_noop_without_a_device():
+    """The NUMA helper never raises: without a CUDA device (or NVML) it reports 0 bound cores and leaves the
+    process affinity alone."""
+    import os
+    import torch
+    from snowmocap_b200.dist import bind_host_to_gpu
+    if torch.cuda.is_available():
+        pytest.skip("CPU-side check")
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu(0) == 0
+    assert os.sched_getaffinity(0) == before
