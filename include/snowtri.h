@@ -212,6 +212,15 @@ int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smooth_t* s, do
                                    const int* d_nout, int* d_nsmooth, int F, int Pout, double delta_time,
                                    void* stream);
 
+/* The per-frame body of the reference's main.py (:55-87) for a whole clip in one call: snowtri_run (keypoint_num = J)
+ * -> snowtri_smooth_run (if sm != NULL) -> snowtri_blender_run -> snowtri_blender_smooth_run (if bs != NULL), back to
+ * back on `stream`; arguments as documented at those entry points.  d_nsmooth is required with sm, d_nfinal with bs;
+ * the control points are derived from the persons counted by d_nsmooth (or d_nout without sm). */
+int snowtri_clip_run(snowtri_t* h, snowtri_smooth_t* sm, snowtri_blender_smooth_t* bs, const float* d_kpts,
+                     const float* d_scores, const int* d_counts, int F, int P, int J, int Pout, float* d_out,
+                     float* d_pscores, int* d_nout, int* d_nsmooth, float* d_ctrl, unsigned* d_valid, int* d_nfinal,
+                     double delta_time, void* stream);
+
 /* Final all-gather of the 3D joints across the GPUs of one box (north_star: frames shard across the GPUs, "NCCL
  * over NVLink appears only as a final all-gather of 3D joints").  One process per GPU, one handle per process.
  * NCCL ("libnccl.so.2") is loaded with dlopen at first use.  Either pass the host's own ncclComm_t, or let the handle

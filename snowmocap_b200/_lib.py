@@ -42,6 +42,7 @@ SYMBOLS = {
     "snowtri_blender_smooth_set_chunked": (_I, [_P, _I]),
     "snowtri_blender_smooth_run": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
     "snowtri_blender_smooth_run_f64": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _D, _P]),
+    "snowtri_clip_run": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _D, _P]),
     "snowtri_comm_unique_id": (_I, [_P]),
     "snowtri_comm_init": (_I, [_P, _P, _I, _I]),
     "snowtri_comm_destroy": (_I, [_P]),

@@ -115,6 +115,34 @@ class BlenderSmoothState:
             pass
 
 
+def run_clip(engine, kpts, scores, counts=None, smooth_state=None, blender_smooth_state=None, Pout=None,
+             delta_time=1 / 30):
+    """``snowtri_clip_run``: the per-frame body of the reference's main.py (:55-87) for a whole clip in one C call --
+    triangulate + condense, ``Human_Triangulation_Smooth`` (``smooth_state``: an ``engine.SmoothState`` or None),
+    Blender control points, ``Human_Triangulation_Blender_Smooth`` (``blender_smooth_state`` or None).  Device
+    tensors in, device tensors out: dict(out, pscores, nout, nsmooth, ctrl, valid, nfinal)."""
+    F, C, P, J = engine._check_inputs(kpts, scores, counts)
+    if J < 130:
+        raise IndexError(f"index 129 is out of bounds for axis 0 with size {J}")
+    Pout = P if Pout is None else int(Pout)
+    dev = engine.device
+    res = {"out": torch.empty((F, Pout, J, 4), dtype=torch.float32, device=dev),
+           "pscores": torch.empty((F, Pout), dtype=torch.float32, device=dev),
+           "nout": torch.empty((F,), dtype=torch.int32, device=dev),
+           "nsmooth": torch.empty((F,), dtype=torch.int32, device=dev) if smooth_state is not None else None,
+           "ctrl": torch.empty((F, Pout, 24, 4), dtype=torch.float32, device=dev),
+           "valid": torch.empty((F, Pout), dtype=torch.int32, device=dev),
+           "nfinal": torch.empty((F,), dtype=torch.int32, device=dev) if blender_smooth_state is not None else None}
+    with torch.cuda.device(dev):
+        _lib.check(engine._lib.snowtri_clip_run(
+            engine._h, smooth_state._s if smooth_state is not None else None,
+            blender_smooth_state._s if blender_smooth_state is not None else None,
+            _ptr(kpts), _ptr(scores), _ptr(counts), F, P, J, Pout, _ptr(res["out"]), _ptr(res["pscores"]),
+            _ptr(res["nout"]), _ptr(res["nsmooth"]), _ptr(res["ctrl"]), _ptr(res["valid"]), _ptr(res["nfinal"]),
+            float(delta_time), _stream()), engine._h)
+    return res
+
+
 def _engine():
     from .triangulation import _util_engine
     return _util_engine()

@@ -740,3 +740,26 @@ extern "C" int snowtri_blender_smooth_run_f64(snowtri_t* h, snowtri_blender_smoo
                                               int Pout, double delta_time, void* stream) {
     return blender_smooth_run(h, s, d_ctrl, true, d_valid, d_nout, d_nsmooth, F, Pout, delta_time, stream);
 }
+
+// main.py:55-87 for a clip in one call: the four stages back to back on one stream, nothing returns to the host in
+// between.  Each stage is the entry point of the same name; this only removes the host work between the launches.
+extern "C" int snowtri_clip_run(snowtri_t* h, snowtri_smooth_t* sm, snowtri_blender_smooth_t* bs, const float* d_kpts,
+                                const float* d_scores, const int* d_counts, int F, int P, int J, int Pout, float* d_out,
+                                float* d_pscores, int* d_nout, int* d_nsmooth, float* d_ctrl, unsigned* d_valid,
+                                int* d_nfinal, double delta_time, void* stream) {
+    if (!h) return fail(nullptr, SNOWTRI_E_ARG, "snowtri_clip_run: NULL handle");
+    if (F == 0) return SNOWTRI_OK;
+    if ((sm && !d_nsmooth) || (bs && !d_nfinal)) return fail(h, SNOWTRI_E_ARG, "snowtri_clip_run: NULL count buffer");
+    int rc = snowtri_run(h, d_kpts, d_scores, d_counts, F, P, J, J, Pout, d_out, d_pscores, d_nout, stream);
+    if (rc != SNOWTRI_OK) return rc;
+    const int* counts = d_nout;
+    if (sm) {
+        rc = snowtri_smooth_run(h, sm, d_out, d_nout, d_nsmooth, F, Pout, J, delta_time, stream);
+        if (rc != SNOWTRI_OK) return rc;
+        counts = d_nsmooth;
+    }
+    rc = snowtri_blender_run(h, d_out, counts, F, Pout, J, d_ctrl, d_valid, stream);
+    if (rc != SNOWTRI_OK) return rc;
+    if (bs) rc = snowtri_blender_smooth_run(h, bs, d_ctrl, d_valid, counts, d_nfinal, F, Pout, delta_time, stream);
+    return rc;
+}
