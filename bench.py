@@ -8,7 +8,10 @@ that is larger than L2, already resident in HBM.  `value` = F*P*J*K / device tim
 max over ranks).  `e2e` is the same metric through the host-buffer C-ABI call
 (snowtri_run_host: pinned host -> device, kernel, device -> host every step).
 Multi-GPU: frames shard across ranks (weak scaling, no data-path collective); the final
-all-gather of the 3D joints that north_star mentions is timed once, outside the steps.
+all-gather of the 3D joints that north_star mentions is timed once, outside the steps
+(`allgather`: torch.distributed and, under `c_abi`, snowtri_allgather checked against it).
+`downstream` (N=1): ms per batch of the later per-frame stages of the reference's main.py on the
+step's output, device-resident: snowtri_smooth_run, snowtri_blender_run, snowtri_blender_smooth_run.
 `--impl reference` times the CPU restatement of the reference's own implementation
 (oracle/loop_oracle.py: per-keypoint np.linalg.inv, per-pair 2x2 solve) on all host cores.
 """
