@@ -76,6 +76,39 @@ def test_oracle_smooth_matches_reference_golden():
         np.testing.assert_allclose(np.nan_to_num(y), np.nan_to_num(want), rtol=0, atol=1e-13)
 
 
+def test_oracle_control_points_are_rigid_motion_equivariant():
+    """Moving the person by a rotation Q and a translation t moves every position by the same motion and composes
+    the root rotation with Q (a property of blender.py:11-96 that needs no reference run)."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+    pts = _persons(rng, 6).astype(np.float64)
+    pos = [k for k in range(24) if k != bo.ROOT_ROTATION]
+    for n in range(6):
+        Q = Rotation.random(random_state=100 + n)
+        t = rng.uniform(-3, 3, 3)
+        c0, v0 = bo.control_points(pts[n])
+        c1, v1 = bo.control_points(Q.apply(pts[n]) + t)
+        assert v0.all() and v1.all()
+        np.testing.assert_allclose(c1[pos, :3], Q.apply(c0[pos, :3]) + t, atol=1e-11)
+        q0 = Rotation.from_quat(np.roll(c0[1], -1))     # stored (w, x, y, z) -> SciPy's (x, y, z, w)
+        q1 = Rotation.from_quat(np.roll(c1[1], -1))
+        np.testing.assert_allclose(q1.as_matrix(), (Q * q0).as_matrix(), atol=1e-11)
+
+
+def test_oracle_smoothing_is_linear_in_the_inputs():
+    """With every control point valid the followers are a linear filter: step(a*x + b*y) = a*step(x) + b*step(y)."""
+    rng = np.random.default_rng(13)
+    _, fzr = _profiles()
+    x = rng.normal(size=(30, 2, 24, 4))
+    y = rng.normal(size=(30, 2, 24, 4))
+    valid = np.ones((2, 24), bool)
+    ox, oy, oz = bo.BlenderSmoothOracle(fzr), bo.BlenderSmoothOracle(fzr), bo.BlenderSmoothOracle(fzr)
+    for t in range(30):
+        sx, sy = ox.step(x[t], valid, 1 / 30), oy.step(y[t], valid, 1 / 30)
+        sz = oz.step(2.0 * x[t] - 0.5 * y[t], valid, 1 / 30)
+        np.testing.assert_allclose(sz, 2.0 * sx - 0.5 * sy, atol=1e-11)
+
+
 # ---- CPU: host logic of the drop-in names (no device is touched on these paths) --------------------------------
 def test_dropin_host_checks_run_before_the_device_is_needed():
     from snowmocap_b200 import Human_Triangulation_Blender, Human_Triangulation_To_Blender_Result
