@@ -244,6 +244,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="multi-GPU: do not bind each rank to its GPU's NUMA node")
     ap.add_argument("--no-others", action="store_true", help="skip the short runs of the other precision modes")
+    ap.add_argument("--general-gen", type=int, default=2, choices=[1, 2],
+                    help="several persons per camera: 2 = second-generation kernels (default), 1 = first generation")
     ap.add_argument("--jit", default="auto", choices=["off", "auto", "always"],
                     help="rig-specialised single-person kernel compiled at run time (NVRTC)")
     args = ap.parse_args()
@@ -278,6 +280,7 @@ def main():
         args.precision = "f32" if P == 1 else "f64"
     eng = TriangulationEngine(rig.K, rig.R, rig.t, device=local, precision=args.precision, **prm)
     eng.set_jit(args.jit)
+    eng.set_general_kernels(args.general_gen)
     kpts, scores = synth.make_frames_torch(rig, F, P, J, seed=1234 + rank, device=dev)
     out = {"out": torch.empty((F, pout, J, 4), dtype=torch.float32, device=dev),
            "pscores": torch.empty((F, pout), dtype=torch.float32, device=dev),

@@ -73,6 +73,12 @@ int snowtri_set_precision(snowtri_t* h, int precision);
  * warp-autonomous single-person kernel, where frames_per_group is the frames per warp tile (<= 32);
  * any non-zero `threads` (-1 = "automatic block size") selects the general fused kernel instead. */
 int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ctas, int threads);
+/* Several persons per camera, float modes: 2 (default) = second-generation kernels of the streaming general path
+ * (matching + centres in one launch, clustering + member decode, clique fuse + person score: 3 launches per chunk);
+ * 1 = the first-generation kernels (6 launches), kept for the all-float64 mode and for comparisons.
+ * snowtri_last_kernel() says which ran: "general2" (both new kernels), "general2m" (new matching, first-generation
+ * fuse: more than 8 cameras) or "general". */
+int snowtri_set_general_kernels(snowtri_t* h, int generation);
 
 /* Fused hot path for a batch of F frames: rays -> all camera-pair x person-pair candidates ->
  * gating -> greedy clustering -> score-weighted fuse (main.py:55-71 for every frame).
@@ -240,7 +246,7 @@ int snowtri_allgather(snowtri_t* h, const void* d_send, void* d_recv, size_t byt
 const char* snowtri_last_error(snowtri_t* h);       /* also valid with h == NULL (create failures) */
 long long snowtri_launch_count(snowtri_t* h);       /* kernels launched through this handle so far */
 int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group);
-const char* snowtri_last_kernel(snowtri_t* h);      /* "p1", "p1-jit", "general", "fused" or "fused-fly"; "" before any run */
+const char* snowtri_last_kernel(snowtri_t* h);      /* "p1", "p1-jit", "general", "general2", "general2m", "fused" or "fused-fly"; "" before any run */
 int snowtri_version(void);
 
 #ifdef __cplusplus

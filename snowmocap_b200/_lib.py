@@ -19,6 +19,7 @@ SYMBOLS = {
     "snowtri_set_precision": (_I, [_P, _I]),
     "snowtri_set_tuning": (_I, [_P, _I, _I, _I]),
     "snowtri_set_pipeline": (_I, [_P, _I]),
+    "snowtri_set_general_kernels": (_I, [_P, _I]),
     "snowtri_set_jit": (_I, [_P, _I]),
     "snowtri_jit_status": (ct.c_char_p, [_P]),
     "snowtri_run": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

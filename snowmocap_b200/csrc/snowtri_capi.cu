@@ -106,6 +106,7 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     snowtri_jit_free(h);
     snowtri_comm_destroy(h);
     free(h->p1_args);
+    free(h->mf_args);
     if (h->pipe_in) {
         cudaStreamDestroy(h->pipe_in);
         cudaStreamDestroy(h->pipe_out);
@@ -155,6 +156,13 @@ extern "C" int snowtri_set_tuning(snowtri_t* h, int frames_per_group, int max_ct
     return SNOWTRI_OK;
 }
 
+extern "C" int snowtri_set_general_kernels(snowtri_t* h, int generation) {
+    if (!h || (generation != 1 && generation != 2))
+        return fail(h, SNOWTRI_E_ARG, "snowtri_set_general_kernels: generation must be 1 or 2");
+    h->gen1_only = generation == 1 ? 1 : 0;
+    return SNOWTRI_OK;
+}
+
 extern "C" int snowtri_set_jit(snowtri_t* h, int mode) {
     if (!h || mode < 0 || mode > 2) return fail(h, SNOWTRI_E_ARG, "snowtri_set_jit: mode must be 0 (off), 1 (auto) or 2 (always)");
     h->jit_mode = mode;
@@ -174,7 +182,8 @@ extern "C" long long snowtri_launch_count(snowtri_t* h) { return h ? h->launches
 extern "C" const char* snowtri_last_kernel(snowtri_t* h) {
     if (!h || h->launches == 0) return "";
     if (h->last_fly == 4) return "p1-jit";
-    return h->last_fly == 3 ? "general" : (h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused"));
+    if (h->last_fly == 3) return h->last_gen2 == 3 ? "general2" : (h->last_gen2 == 1 ? "general2m" : "general");
+    return h->last_fly == 2 ? "p1" : (h->last_fly == 1 ? "fused-fly" : "fused");
 }
 
 extern "C" int snowtri_last_launch_info(snowtri_t* h, int* grid, int* block, int* smem_bytes, int* frames_per_group) {

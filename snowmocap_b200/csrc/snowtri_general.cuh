@@ -27,6 +27,12 @@
 
 namespace snowtri {
 
+struct GenDesc {               // one output row (frame, slot) of the second-generation fuse (snowtri_mfuse.cuh)
+    unsigned long long obs;    // byte c: person index of camera c in this cluster, 0xff = camera not in the cluster
+    int n;                     // members (reference :148 divides by it)
+    int start;                 // offset of the member list in the frame's memb2 block; bit 31 set: clique
+};
+
 struct GenArgs {
     const float* kpts;    // (F,C,P,J,2)
     const float* scores;  // (F,C,P,J)
@@ -48,6 +54,8 @@ struct GenArgs {
     int* cstart;          // (F,ncand)
     int* cn;              // (F,ncand)
     int* kcount;          // (F)
+    uint2* memb2;         // (F,ncand) decoded members, written by the clustering kernels when non-null
+    GenDesc* desc;        // (F,Pout) row descriptors, written by the clustering kernels when non-null
 };
 
 constexpr int kGenWarps = 8;  // warps per CTA of K1/K3/K4
@@ -242,6 +250,63 @@ __global__ void __launch_bounds__(256) gen_centre_kernel(const __grid_constant__
     c3[2] = w.z;
 }
 
+// ---- tail of the clustering kernels (second generation): decode every cluster member once and recognise CLIQUE
+// clusters -- one observation per camera and every pair of the observed cameras present, i.e. what a correctly matched
+// person is.  Called by all `nthreads` threads of the frame's CTA (or the 32 lanes of its warp) after the frame's
+// member lists are complete and visible.
+//   memb2[i].x = row of the main ray      (mc*P + pm) | mc << 24
+//   memb2[i].y = row of the secondary ray (sc*P + ps) | sc << 24        (rows < 2^24, cameras < 2^8)
+__device__ __forceinline__ void gen_describe(const GenArgs& a, int f, int K, int tid, int nthreads) {
+    const size_t o = (size_t)f * a.ncand;
+    const int P = a.P, PP = P * P, C = a.C;
+    const int total = K > 0 ? a.cstart[o + K - 1] + a.cn[o + K - 1] : 0;
+    for (int i = tid; i < total; i += nthreads) {
+        const int c = (int)a.memb[o + i];
+        const int pair = c / PP, pm = (c / P) % P, ps = c % P;
+        int mc, sc;
+        decode_pair(pair, C, mc, sc);
+        a.memb2[o + i] = make_uint2((uint32_t)(mc * P + pm) | ((uint32_t)mc << 24), (uint32_t)(sc * P + ps) | ((uint32_t)sc << 24));
+    }
+    if (!a.desc) return;
+    const int lane = tid & 31, warp = tid >> 5, nw = nthreads >> 5;
+    const int rows = min(K, a.Pout);
+    for (int k = warp; k < rows; k += nw) {
+        const int n = a.cn[o + k], st = a.cstart[o + k];
+        bool clique = C <= 8 && n <= 28 && P <= 255;
+        unsigned long long obs = ~0ull;
+        if (clique) {  // every member sits in one lane
+            int mc = -1, sc = -1, pm = 0, ps = 0;
+            if (lane < n) {
+                const int c = (int)a.memb[o + st + lane];
+                pm = (c / P) % P;
+                ps = c % P;
+                decode_pair(c / PP, C, mc, sc);
+            }
+            bool bad = false;
+            int ncam = 0;
+            for (int c = 0; c < C; ++c) {
+                const bool hit_m = mc == c, hit_s = sc == c;
+                const int person = hit_m ? pm : ps;
+                const unsigned hit = __ballot_sync(kFull, hit_m || hit_s);
+                if (hit) {
+                    const int ob = __shfl_sync(kFull, person, __ffs(hit) - 1);
+                    bad |= __ballot_sync(kFull, (hit_m || hit_s) && person != ob) != 0u;
+                    ++ncam;
+                    obs = (obs & ~(0xffull << (8 * c))) | ((unsigned long long)(ob & 0xff) << (8 * c));
+                }
+            }
+            clique = !bad && n == ncam * (ncam - 1) / 2;
+        }
+        if (lane == 0) {
+            GenDesc d;
+            d.obs = obs;
+            d.n = n;
+            d.start = st | (clique ? (int)0x80000000 : 0);
+            a.desc[(size_t)f * a.Pout + k] = d;
+        }
+    }
+}
+
 // ---- K2 ------------------------------------------------------------------------------------------------------
 // Large candidate counts: one CTA per frame.
 __global__ void __launch_bounds__(256) gen_cluster_block_kernel(const __grid_constant__ GenArgs a) {
@@ -251,6 +316,10 @@ __global__ void __launch_bounds__(256) gen_cluster_block_kernel(const __grid_con
     const int K = cluster_block<256>(a.ncand, a.keep + o, a.klist + o, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o,
                                      a.cn + o, wtmp, a.tol2, a.prm.num_tol);
     if (threadIdx.x == 0) a.kcount[f] = K;
+    if (a.memb2) {  // cluster_block ends with a barrier: the lists are visible to the whole CTA
+        __syncthreads();
+        gen_describe(a, f, K, threadIdx.x, 256);
+    }
 }
 
 // Small candidate counts: one warp per frame.
@@ -273,6 +342,10 @@ __global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const 
     const int K = cluster_warp(nk, kl, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o, a.cn + o, a.tol2,
                                a.prm.num_tol, lane);
     if (lane == 0) a.kcount[f] = K;
+    if (a.memb2) {
+        __syncwarp();
+        gen_describe(a, f, K, lane, 32);
+    }
 }
 
 // ---- K2b: decode every cluster member once: dense candidate index -> (main row, secondary row, pair) -------

@@ -40,6 +40,10 @@ struct snowtri_handle {
     void* gen_scratch;        // candidate scratch of the streaming general path
     size_t gen_scratch_bytes;
     void* p1_args;            // host copy of the single-person kernel's argument block
+    void* mf_args;            // host copy of the multi-person fuse kernel's argument block
+    size_t mf_args_bytes;
+    int gen1_only;            // tests / comparisons: first-generation general kernels only
+    int last_gen2;            // bit 0: second-generation match kernel ran, bit 1: second-generation fuse
     size_t p1_args_bytes;
     int jit_mode;             // 0 off, 1 auto (long batches), 2 always
     void* jit_cache;          // rig-specialised kernels (snowtri_jit.cu)

@@ -91,6 +91,30 @@ uint64_t fnv1a(const std::string& s) {
     return h;
 }
 
+// FNV-1a of the two headers the generated translation unit includes, as they were when the library was built
+// (snowtri_build_stamp.h is written by snowmocap_b200/build.py).  A stale or edited csrc/ next to the library would
+// give the JIT kernel another P1Args layout than the host code fills in.
+#include "snowtri_build_stamp.h"
+bool headers_match_build(const std::string& dir, char* why, size_t n) {
+    uint64_t hsh = 1469598103934665603ull;
+    const char* files[] = {"/snowtri_math.cuh", "/snowtri_p1.cuh"};
+    for (const char* f : files) {
+        FILE* fp = fopen((dir + f).c_str(), "rb");
+        if (!fp) {
+            snprintf(why, n, "failed: %s%s not readable", dir.c_str(), f);
+            return false;
+        }
+        int ch;
+        while ((ch = fgetc(fp)) != EOF) hsh = (hsh ^ (unsigned char)ch) * 1099511628211ull;
+        fclose(fp);
+    }
+    if (hsh != SNOWTRI_P1_HEADERS_FNV) {
+        snprintf(why, n, "failed: csrc/snowtri_p1.cuh or snowtri_math.cuh differs from the build of this library");
+        return false;
+    }
+    return true;
+}
+
 std::string csrc_dir() {
     Dl_info info;
     if (!dladdr((void*)&snowtri_version, &info) || !info.dli_fname) return "";
@@ -104,8 +128,10 @@ std::string csrc_dir() {
 void snowtri_jit_free(snowtri_t* h) {
     Cache* c = (Cache*)h->jit_cache;
     if (!c) return;
-    if (g_api.ok)
+    if (g_api.ok) {
+        cudaDeviceSynchronize();  // a kernel of these modules may still be running on a caller stream
         for (int i = 0; i < c->n; ++i) g_api.unload(c->e[i].mod);
+    }
     free(c);
     h->jit_cache = nullptr;
 }
@@ -137,6 +163,7 @@ void* snowtri_jit_get(snowtri_t* h, const std::string& source, const char* name,
             snprintf(h->jit_status, sizeof(h->jit_status), "failed: cannot locate csrc/ next to the library");
             return nullptr;
         }
+        if (!headers_match_build(dir, h->jit_status, sizeof(h->jit_status))) return nullptr;
         void* prog = nullptr;
         if (g_api.create(&prog, source.c_str(), "snowtri_p1_jit.cu", 0, nullptr, nullptr) != 0) {
             snprintf(h->jit_status, sizeof(h->jit_status), "failed: nvrtcCreateProgram");
@@ -167,7 +194,8 @@ void* snowtri_jit_get(snowtri_t* h, const std::string& source, const char* name,
             if (mod) g_api.unload(mod);
             return nullptr;
         }
-        if (c->n == 8) {  // cache full: drop the oldest
+        if (c->n == 8) {  // cache full: drop the oldest -- after every launch of it has finished
+            cudaDeviceSynchronize();
             g_api.unload(c->e[0].mod);
             memmove(&c->e[0], &c->e[1], 7 * sizeof(Entry));
             c->n = 7;

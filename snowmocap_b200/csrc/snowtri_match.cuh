@@ -1,0 +1,260 @@
+// Streaming general path, second generation of its two hot kernels (float32 bulk / float64 decisions, "mixed"):
+//
+//   gen_match_*_kernel   cross-camera person matching = the keep decision of every (camera pair, person pair)
+//                        candidate (reference triangulation.py:56-87) AND the float64 centre-joint midpoint of the
+//                        kept ones (:112,124) in one launch (was gen_keep_kernel + gen_centre_kernel).
+//
+// Why it is faster than gen_keep_kernel (profiles/r1e/gen_keep_cfg3_mixed_ncu_summary.txt: 93 warp-instructions per
+// 32 joint evaluations, 5 % of them local-memory traffic):
+//   * rays are built ONCE per frame -- (x, y, z, |h|^2) as one float4, the sign of |h|^2 carrying "score below the
+//     keypoint threshold" -- into shared memory (frames that fit) or a scratch array (large rigs), instead of 6 FMAs
+//     per ray per use;
+//   * a warp owns a 4 x 4 tile of (main person, secondary person) candidates of one camera pair; a lane holds the
+//     4 + 4 rays of its joint in registers and evaluates the 16 candidates from them: 0.5 ray loads per evaluation,
+//     the per-main-ray part of the triple product (d x hm) hoisted out of the 4 secondary persons;
+//   * the gate needs no cross product:  d.(hm x hs) = hs.(d x hm)  and  |hm x hs|^2 = |hm|^2 |hs|^2 - (hm.hs)^2,
+//     10 FMA-class operations per evaluation;
+//   * 16 running sums per lane in registers (static indices only: nothing in local memory), ONE butterfly reduction
+//     per tile (16 + 4x5 shuffles) instead of two 5-step reductions per candidate;
+//   * the decision, its float64 re-evaluation when the float32 sum is closer to the threshold than its error bound,
+//     and the float64 centre of the kept candidates happen in the same warp, so the keep byte and the centre are the
+//     only things written.
+// Discrete decisions stay exact: same error-bound logic as gen_keep_item (kDistDelta, guard band on the gate), and
+// anything that turns the float32 sum into NaN (non-finite inputs, parallel rays) falls into the float64 path.
+// Requires dthr > 0 (the sign trick for low scores needs a positive gate limit); the host keeps the first-generation
+// kernels for dthr <= 0 and for the all-float64 mode.
+#pragma once
+#include "snowtri_general.cuh"
+
+namespace snowtri {
+
+constexpr int kTile = 4;  // persons per side of a register tile
+
+// (x, y, z, +-|h|^2) of every ray of a chunk of frames: pre-pass of the large-rig variant
+__global__ void __launch_bounds__(256) gen_rays_kernel(const __grid_constant__ GenArgs a, float4* __restrict__ rays) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* camM = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < a.C * 9; i += blockDim.x) camM[i] = (float)a.cam[(i / 9) * 12 + (i % 9)];
+    __syncthreads();
+    const size_t R = (size_t)a.C * a.P * a.J, n = (size_t)a.F * R;
+    const float2* kf = reinterpret_cast<const float2*>(a.kpts);
+    const int PJ = a.P * a.J;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)((i % R) / PJ);
+        const float2 q = __ldg(kf + i);
+        const float s = __ldg(a.scores + i);
+        const V3<float> h = back_project<float>(camM + 9 * c, q.x, q.y);
+        const float cc = dot3(h, h);
+        rays[i] = make_float4(h.x, h.y, h.z, s < a.prm.kst_f ? -cc : cc);
+    }
+}
+
+// After the call lane l holds the warp-wide sum of v[(l >> 1) & 15] (both lanes of a pair hold the same value).
+// Halving butterfly: 8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5; fixed summation order.
+__device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int w = 8; w >= 1; w >>= 1) {
+        const bool hi = (lane & (2 * w)) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = hi ? v[i] : v[i + w];
+            const float keep = hi ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, 2 * w);
+        }
+    }
+    return v[0] + __shfl_xor_sync(kFull, v[0], 1);
+}
+
+// One (frame, camera pair, 4 x 4 person tile) item by one warp.  `rays` / `scs` point at the frame's rays and
+// scores (shared or global memory), kf / sf at its raw inputs in global memory (float64 paths).
+__device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
+                                               const float* scs, const float2* kf, const float* sf, int f, int it, int lane) {
+    const int C = a.C, P = a.P, J = a.J;
+    const int tpp = (P + kTile - 1) / kTile;
+    const int pair = it / (tpp * tpp), tt = it - pair * tpp * tpp;
+    const int pm0 = (tt / tpp) * kTile, ps0 = (tt % tpp) * kTile;
+    const int mc = pairs[pair].x, sc = pairs[pair].y;
+    const int cm = a.counts ? max(0, min(P, a.counts[(size_t)f * C + mc])) : P;
+    const int cs = a.counts ? max(0, min(P, a.counts[(size_t)f * C + sc])) : P;
+    const int nm = max(0, min(kTile, cm - pm0)), ns = max(0, min(kTile, cs - ps0));  // persons present in the tile
+    // lanes 2c and 2c+1 end up with candidate c = (i, k) of the tile
+    const int ci = (lane >> 3) & 3, ck = (lane >> 1) & 3;
+    const bool present = ci < nm && ck < ns;
+    bool kept = present;
+
+    if (!a.all_kept && nm > 0 && ns > 0) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
+        float sum[kTile * kTile], err[kTile];
+#pragma unroll
+        for (int i = 0; i < kTile * kTile; ++i) sum[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < kTile; ++i) err[i] = 0.f;
+        V3<float> d;
+        d.x = (float)(camD[12 * sc + 9] - camD[12 * mc + 9]);
+        d.y = (float)(camD[12 * sc + 10] - camD[12 * mc + 10]);
+        d.z = (float)(camD[12 * sc + 11] - camD[12 * mc + 11]);
+        const float dthr2 = (float)(a.prm.dthr * a.prm.dthr);
+        const float4* rm = rays + (size_t)(mc * P + pm0) * J;
+        const float4* rs = rays + (size_t)(sc * P + ps0) * J;
+        const float* qm = scs + (size_t)(mc * P + pm0) * J;
+        const float* qs = scs + (size_t)(sc * P + ps0) * J;
+        for (int j0 = 0; j0 < J; j0 += 32) {  // every lane stays in the loop: the slow path is behind a vote
+            const bool valid = j0 + lane < J;
+            const int j = valid ? j0 + lane : J - 1;
+            float4 m[kTile], s[kTile];
+            float sm[kTile], ss[kTile];
+#pragma unroll
+            for (int i = 0; i < kTile; ++i) {  // persons beyond the count alias person 0 of the tile and are masked
+                const int r = i < nm ? i : 0;
+                m[i] = rm[(size_t)r * J + j];
+                sm[i] = qm[(size_t)r * J + j];
+            }
+#pragma unroll
+            for (int k = 0; k < kTile; ++k) {
+                const int r = k < ns ? k : 0;
+                s[k] = rs[(size_t)r * J + j];
+                ss[k] = qs[(size_t)r * J + j];
+                if (k >= ns) s[k].w = -1.f;
+            }
+#pragma unroll
+            for (int i = 0; i < kTile; ++i) {
+                const bool lowm = !valid || i >= nm || m[i].w < 0.f;
+                V3<float> e;  // d x hm:  d.(hm x hs) = hs.(d x hm)
+                e.x = fmaf(d.y, m[i].z, -(d.z * m[i].y));
+                e.y = fmaf(d.z, m[i].x, -(d.x * m[i].z));
+                e.z = fmaf(d.x, m[i].y, -(d.y * m[i].x));
+#pragma unroll
+                for (int k = 0; k < kTile; ++k) {
+                    const float B = fmaf(m[i].x, s[k].x, fmaf(m[i].y, s[k].y, m[i].z * s[k].z));
+                    const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
+                    // |hm x hs|^2; a secondary ray with a low score carries -|hs|^2: nn < 0, lim < 0 <= dn2, gated
+                    const float nn = fmaf(m[i].w, s[k].w, -(B * B));
+                    const float dn2 = dn * dn, lim = dthr2 * nn;
+                    const bool pass = !lowm && !(dn2 > lim);  // dist > dthr is gated (strict); NaN is not (Q8/Q9)
+                    const bool near = !lowm && fabsf(dn2 - lim) < (2.f * kGateGuard) * lim;
+                    if (__any_sync(kFull, pass || near)) {
+                        const float rd = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);  // sqrt(n.n)/|d.n| = 1/dist
+                        const float w = (sm[i] + ss[k]) * 0.0005f * rd;
+                        // error bound in units of kDistDelta: score/dist, plus the whole score of a joint whose
+                        // gate could flip (shared by the 4 candidates of a main person: a larger bound is still a bound)
+                        if (pass) {
+                            sum[i * kTile + k] += w;
+                            err[i] = fmaf(w, rd, err[i]);
+                        }
+                        if (near) err[i] = fmaf(w, 1.0f / kDistDelta, err[i]);
+                    }
+                }
+            }
+        }
+        const float tot = reduce16(sum, lane);
+#pragma unroll
+        for (int i = 0; i < kTile; ++i) err[i] = warp_sum(err[i]);
+        const float e = ci == 0 ? err[0] : (ci == 1 ? err[1] : (ci == 2 ? err[2] : err[3]));
+        // mean < ast  <=>  sum < ast*J; the float32 sum decides unless it sits on the threshold
+        const double thrJ = a.prm.ast * (double)J, gap = fabs((double)tot - thrJ);
+        kept = present && !((double)tot < thrJ);  // NaN mean is kept (Q9)
+        const double slack = (double)kDistDelta * (double)e + 4e-5 * fabs((double)tot);
+        unsigned redo = __ballot_sync(kFull, present && !(lane & 1) && !(gap > slack));
+        while (redo) {  // discrete decision: the whole warp redoes this candidate in float64 from the raw inputs
+            const int l = __ffs(redo) - 1;
+            redo &= redo - 1;
+            const int cc = l >> 1;
+            const double mean = gen_candidate_mean_f64(a, camD, kf, sf, mc, pm0 + (cc >> 2), sc, ps0 + (cc & 3), lane);
+            if ((lane >> 1) == cc) kept = !(mean < a.prm.ast);
+        }
+    }
+
+    // keep byte of every candidate slot of the tile, float64 centre-joint midpoint of the kept ones (reference :112,124)
+    const int pm = pm0 + ci, ps = ps0 + ck;
+    if (!(lane & 1) && pm < P && ps < P) {
+        const size_t n = (size_t)f * a.ncand + ((size_t)pair * P + pm) * P + ps;
+        a.keep[n] = kept ? 1 : 0;
+        if (kept) {
+            const float2 q0 = kf[(size_t)(mc * P + pm) * J + a.prm.center], q1 = kf[(size_t)(sc * P + ps) * J + a.prm.center];
+            const double* c0 = camD + 12 * mc;
+            const double* c1 = camD + 12 * sc;
+            const V3<double> h0 = back_project<double>(c0, (double)q0.x, (double)q0.y);
+            const V3<double> h1 = back_project<double>(c1, (double)q1.x, (double)q1.y);
+            V3<double> dd, mid;
+            dd.x = c1[9] - c0[9]; dd.y = c1[10] - c0[10]; dd.z = c1[11] - c0[11];
+            mid.x = (c0[9] + c1[9]) / 2; mid.y = (c0[10] + c1[10]) / 2; mid.z = (c0[11] + c1[11]) / 2;
+            const PairSol<double> sol = pair_solve(h0, h1, dd);
+            const V3<double> w = pair_midpoint(sol, h0, h1, mid);
+            double* c3 = a.cen + n * 3;
+            c3[0] = w.x;
+            c3[1] = w.y;
+            c3[2] = w.z;
+        }
+    }
+}
+
+// Shared-memory tables of the match kernels: camera matrices and centres in float64 (C*12), the pair table.
+struct MatchTables {
+    const double* camD;
+    const uchar2* pairs;
+    __device__ MatchTables(unsigned char* smem, const GenArgs& a) {
+        double* cd = reinterpret_cast<double*>(smem);
+        uchar2* pr = reinterpret_cast<uchar2*>(cd + a.C * 12);
+        camD = cd;
+        pairs = pr;
+        for (int i = threadIdx.x; i < a.C * 12; i += blockDim.x) cd[i] = a.cam[i];
+        for (int p = threadIdx.x; p < a.npairs; p += blockDim.x) {
+            int mc, sc;
+            decode_pair(p, a.C, mc, sc);
+            pr[p] = make_uchar2((unsigned char)mc, (unsigned char)sc);
+        }
+    }
+    __host__ __device__ static size_t bytes(int C, int npairs) { return (((size_t)C * 96 + (size_t)npairs * 2) + 15) & ~(size_t)15; }
+};
+
+// Frames whose rays fit in shared memory (20 bytes per ray): one CTA per frame builds them once and its warps walk the
+// (camera pair, tile) items out of shared memory.  Two CTAs per SM: one CTA's ray build (global loads) and decisions
+// overlap the other's arithmetic.
+__global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    MatchTables tb(smem, a);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    const int f = blockIdx.x, C = a.C, P = a.P, J = a.J;
+    const int R = C * P * J;
+    float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs));
+    float* scs = reinterpret_cast<float*>(rays + R);
+    const float2* kf = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R;
+    const float* sf = a.scores + (size_t)f * R;
+    for (int row = warp; row < C * P; row += NW) {  // one (camera, person) row per warp
+        float M[9];
+        const int c = row / P;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) M[i] = (float)a.cam[12 * c + i];
+        for (int j = lane; j < J; j += 32) {
+            const int i = row * J + j;
+            const float2 q = __ldg(kf + i);
+            const float s = __ldg(sf + i);
+            const V3<float> h = back_project<float>(M, q.x, q.y);
+            const float cc = dot3(h, h);
+            rays[i] = make_float4(h.x, h.y, h.z, s < a.prm.kst_f ? -cc : cc);
+            scs[i] = s;
+        }
+    }
+    __syncthreads();
+    const int tpp = (P + kTile - 1) / kTile;
+    const int items = a.npairs * tpp * tpp;
+    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it, lane);
+}
+
+// Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident
+// while the frame is worked on); one warp per (frame, camera pair, tile).
+__global__ void __launch_bounds__(kGenWarps * 32, 2) gen_match_global_kernel(const __grid_constant__ GenArgs a, const float4* __restrict__ rays) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    MatchTables tb(smem, a);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tpp = (a.P + kTile - 1) / kTile;
+    const long long per_frame = (long long)a.npairs * tpp * tpp;
+    const long long item = (long long)blockIdx.x * kGenWarps + warp;
+    if (item >= (long long)a.F * per_frame) return;
+    const int f = (int)(item / per_frame), it = (int)(item - (long long)f * per_frame);
+    const size_t R = (size_t)a.C * a.P * a.J;
+    gen_match_item(a, tb.camD, tb.pairs, rays + (size_t)f * R, a.scores + (size_t)f * R,
+                   reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f, it, lane);
+}
+
+}  // namespace snowtri

@@ -139,11 +139,9 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
         sy[c] = y[c];
         syd[c] = yd[c];
     }
-    __syncthreads();
-    if (lead) {
-        a.state[0] = init ? 1.0 : 0.0;
-        a.state[1] = (double)n0;
-    }
+    // The clip header (state[0] = seeded, state[1] = persons of the first frame) is read by every block at entry, so
+    // it is NOT rewritten here: a block that starts after block 0 has finished would see the new header on the
+    // clip's first frame.  smooth_finish_kernel, launched behind this kernel on the same stream, writes it.
 }
 
 
@@ -464,8 +462,9 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
     if (F <= 2 * kChunk || s->sequential) {  // short batch: one sequential launch
         if (f64) smooth_kernel<double4><<<grid, 128, 0, st>>>(a);
         else smooth_kernel<float4><<<grid, 128, 0, st>>>(a);
+        smooth_finish_kernel<<<1, 1, 0, st>>>(s->d_state, d_nout, Pout, s->P);
         CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
+        h->launches += 2;
         return SNOWTRI_OK;
     }
     // chunk-parallel path

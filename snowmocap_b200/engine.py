@@ -77,6 +77,10 @@ class TriangulationEngine:
     def set_tuning(self, frames_per_group=0, max_ctas=0, threads=0):
         _lib.check(self._lib.snowtri_set_tuning(self._h, int(frames_per_group), int(max_ctas), int(threads)), self._h)
 
+    def set_general_kernels(self, generation=2):
+        """Several persons per camera, float modes: 2 = second-generation kernels (3 launches per chunk), 1 = the first."""
+        _lib.check(self._lib.snowtri_set_general_kernels(self._h, int(generation)), self._h)
+
     def set_jit(self, mode="auto"):
         """Rig-specialised single-person kernel compiled at run time with NVRTC: "off", "auto" (long batches) or "always"."""
         _lib.check(self._lib.snowtri_set_jit(self._h, {"off": 0, "auto": 1, "always": 2}[mode]), self._h)

@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 def golden_names():
     return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                  if not p.endswith("floor_rig.npz") and not os.path.basename(p).startswith(("smooth_", "blender_", "pipeline_")))
+                  if not p.endswith("floor_rig.npz") and not os.path.basename(p).startswith(("smooth_", "blender_", "pipeline_", "big_")))
 
 
 def smooth_golden_names():
@@ -37,6 +37,26 @@ class Golden:
         self.F = self.kpts.shape[0]
         self.tri = [(z[f"tri_pts_{f}"], z[f"tri_ks_{f}"], z[f"tri_ps_{f}"]) for f in range(self.F)]
         self.con = [(z[f"con_pts_{f}"], z[f"con_ks_{f}"], z[f"con_ps_{f}"]) for f in range(self.F)]
+
+
+class BigGolden:
+    """One fixture written by tests/golden/make_golden_big.py: the real reference's condensed output at a full
+    multi-person size (inputs, candidate count and candidate person scores, condensed persons)."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.name = name
+        self.K, self.R, self.t = z["K"], z["R"], z["t"]
+        self.kpts, self.scores, self.counts = z["kpts"], z["scores"], z["counts"]
+        self.params = json.loads(str(z["params"]))
+        self.F = self.kpts.shape[0]
+        self.tri_ps = [z[f"tri_ps_{f}"] for f in range(self.F)]
+        self.con = [(z[f"con_pts_{f}"], z[f"con_ks_{f}"], z[f"con_ps_{f}"]) for f in range(self.F)]
+        self.seconds_per_frame = float(z["seconds_per_frame"])
+
+
+def big_golden_names():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "big_*.npz")))
 
 
 @pytest.fixture(params=golden_names())

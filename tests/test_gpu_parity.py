@@ -609,13 +609,119 @@ def test_large_rigs_streaming_path(torch_cuda, C, P, F, precision):
     eng = _engine(rig, prm, precision=precision)
     res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=pout)
     torch.cuda.synchronize()
-    assert eng.last_launch_info()["kernel"] == "general"
+    # float modes: second-generation matching kernel (ray pre-pass + tiles from global memory), first-generation fuse
+    assert eng.last_launch_info()["kernel"] == ("general" if precision == "f64" else "general2m")
     out, nout = res["out"].cpu().numpy(), res["nout"].cpu().numpy()
     assert np.array_equal(nout, ref["nout"])
     valid = np.arange(pout)[None, :] < np.minimum(nout, pout)[:, None]
     tol = TOL_FUSED if precision == "f64" else TOL_NORTH_STAR / 10
     assert rel_l2(out[valid][:, :, :3], ref["points"][valid]) < tol
     assert np.array_equal(out[valid][:, :, 3] == 0, ref["kscores"][valid] == 0)
+
+
+# ---- second-generation kernels of the general path (snowtri_match.cuh, snowtri_mfuse.cuh) -----------------------
+def _run_general(torch, rig, d, prm, pout, precision, generation, jout=None, tune_g=0):
+    eng = _engine(rig, prm, precision=precision)
+    eng.set_general_kernels(generation)
+    if tune_g:
+        eng.set_tuning(tune_g, 0, 0)
+    n0 = eng.launch_count
+    res = eng.run(*_to_dev(torch, d["kpts"], d["scores"], d["counts"]), Pout=pout, keypoint_num=jout)
+    torch.cuda.synchronize()
+    return ({k: v.cpu().numpy() for k, v in res.items()}, eng.last_launch_info()["kernel"], eng.launch_count - n0)
+
+
+@pytest.mark.parametrize("C,P,J,F,drop,low", [(8, 4, 133, 40, 0.0, 0.05), (8, 4, 133, 24, 0.25, 0.1), (3, 5, 33, 50, 0.2, 0.1),
+                                              (6, 8, 17, 30, 0.1, 0.3), (4, 2, 133, 64, 0.0, 0.0), (2, 9, 5, 20, 0.3, 0.0),
+                                              (7, 1, 64, 33, 0.2, 0.1), (5, 3, 1, 40, 0.1, 0.0)])
+def test_general_second_generation_vs_oracle_and_first(torch_cuda, C, P, J, F, drop, low):
+    """BASELINE configs[2] geometry and ragged / partial-tile shapes (P not a multiple of the 4 x 4 tile, J below a
+    warp, absent cameras): the three-launch path (matching + centres, clustering + member decode, clique fuse + person
+    score) against the C oracle and against the first-generation six-launch path on the same batch."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(C, seed=C)
+    d = synth.make_frames(rig, F, P, J, seed=900 + C * 10 + P, low_score_frac=low, drop_prob=drop)
+    prm = dict(synth.MULTI_PARAMS, center=min(synth.MULTI_PARAMS["center"], J - 1))
+    pout = min(2 * P, 32)
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    new, kn, ln = _run_general(torch, rig, d, prm, pout, "mixed", 2)
+    old, ko, lo = _run_general(torch, rig, d, prm, pout, "mixed", 1)
+    assert kn == "general2" and ln == 3, (kn, ln)
+    assert ko == "general" and lo == 6, (ko, lo)
+    valid = np.arange(pout)[None, :] < np.minimum(ref["nout"], pout)[:, None]
+    for res, tag in ((new, "gen2"), (old, "gen1")):
+        assert np.array_equal(res["nout"], ref["nout"]), tag
+        assert not res["out"][~valid].any() and not res["pscores"][~valid].any(), tag
+        if valid.any():
+            assert np.array_equal(res["out"][valid][:, :, 3] == 0, ref["kscores"][valid] == 0), tag
+            assert rel_l2(res["out"][valid][:, :, :3], ref["points"][valid]) < TOL_FUSED * 5, tag
+            np.testing.assert_allclose(res["out"][valid][:, :, 3], ref["kscores"][valid], rtol=1e-4, atol=1e-7, err_msg=tag)
+            np.testing.assert_allclose(res["pscores"][valid], ref["pscores"][valid], rtol=1e-4, atol=1e-7, err_msg=tag)
+
+
+@pytest.mark.parametrize("prm_over", [dict(ast=0.0), dict(ast=0.0, cond_tol=10.0), dict(ast=0.05, cond_tol=1.0, num_tol=3),
+                                      dict(dthr=0.01, ast=0.5), dict(kst=0.0, ast=0.3), dict(ast=5.0)])
+def test_general_second_generation_thresholds(torch_cuda, prm_over):
+    """Everything kept (ghost clusters that are not cliques take the rolled member loop), huge merge radius (one
+    cluster with every candidate), cluster-size filter, tight gate, no keypoint threshold, nothing kept."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(6, seed=3)
+    d = synth.make_frames(rig, 48, 3, 133, seed=77, low_score_frac=0.1, drop_prob=0.15)
+    prm = dict(synth.MULTI_PARAMS, **prm_over)
+    pout = 7
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    res, kn, ln = _run_general(torch, rig, d, prm, pout, "mixed", 2)
+    assert kn == "general2" and ln == 3
+    assert np.array_equal(res["nout"], ref["nout"])
+    valid = np.arange(pout)[None, :] < np.minimum(ref["nout"], pout)[:, None]
+    assert not res["out"][~valid].any()
+    if valid.any():
+        assert np.array_equal(res["out"][valid][:, :, 3] == 0, ref["kscores"][valid] == 0)
+        assert rel_l2(res["out"][valid][:, :, :3], ref["points"][valid]) < TOL_NORTH_STAR / 10
+        np.testing.assert_allclose(res["pscores"][valid], ref["pscores"][valid], rtol=2e-4, atol=1e-7)
+
+
+def test_general_second_generation_chunks_and_truncation(torch_cuda):
+    """Several scratch chunks per batch (frames_per_group caps the chunk) and keypoint_num < J give the same bytes /
+    the truncated rows of the one-chunk run."""
+    torch = torch_cuda
+    rig = synth.ring_rig(8)
+    d = synth.make_frames(rig, 70, 4, 133, seed=5, low_score_frac=0.05, drop_prob=0.1)
+    prm = synth.MULTI_PARAMS
+    one, _, l1 = _run_general(torch, rig, d, prm, 8, "mixed", 2)
+    many, _, l2 = _run_general(torch, rig, d, prm, 8, "mixed", 2, tune_g=16)
+    assert l1 == 3 and l2 == 3 * 5
+    assert np.array_equal(one["nout"], many["nout"]) and np.array_equal(one["out"], many["out"])
+    np.testing.assert_allclose(one["pscores"], many["pscores"], rtol=1e-5, atol=1e-7)
+    trunc, _, _ = _run_general(torch, rig, d, dict(prm, center=3), 8, "mixed", 2, jout=40)
+    full, _, _ = _run_general(torch, rig, d, dict(prm, center=3), 8, "mixed", 2)
+    assert np.array_equal(trunc["nout"], full["nout"]) and np.array_equal(trunc["out"], full["out"][:, :, :40])
+
+
+@pytest.mark.parametrize("name", __import__("conftest").big_golden_names())
+@pytest.mark.parametrize("precision", ["f64", "mixed"])
+def test_full_size_reference_goldens(torch_cuda, name, precision):
+    """What the REAL reference emitted at BASELINE configs[2] (8 x 4 x 133, 2 frames) and configs[3] (16 x 8 x 133,
+    1 frame) sizes (tests/golden/make_golden_big.py) against the fused path."""
+    torch = torch_cuda
+    from conftest import BigGolden
+    g = BigGolden(name)
+    pout = max(c[0].shape[0] for c in g.con)
+    if pout > 32:
+        pout = 32
+    eng = _engine(g, g.params, precision=precision)
+    res = eng.run(*_to_dev(torch, g.kpts, g.scores, g.counts), Pout=pout, keypoint_num=g.params["keypoint_num"])
+    torch.cuda.synchronize()
+    out, ps, nout = res["out"].cpu().numpy(), res["pscores"].cpu().numpy(), res["nout"].cpu().numpy()
+    for f in range(g.F):
+        pts, ks, pscore = g.con[f]
+        assert nout[f] == pts.shape[0]
+        n = min(pts.shape[0], pout)
+        assert rel_l2(out[f, :n, :, :3], pts[:n]) < (TOL_FUSED if precision == "f64" else TOL_FUSED * 5)
+        np.testing.assert_allclose(out[f, :n, :, 3], ks[:n], rtol=1e-5 if precision == "f64" else 1e-4, atol=1e-7)
+        np.testing.assert_allclose(ps[f, :n], pscore[:n], rtol=1e-5 if precision == "f64" else 1e-4, atol=1e-7)
 
 
 # ---- empty and degenerate inputs ---------------------------------------------------------------------------------

@@ -61,6 +61,22 @@ def test_c_oracle_fused_matches_reference(golden):
         _check((r["points"][f, :n], r["kscores"][f, :n], r["pscores"][f, :n]), g.con[f], f"{g.name} frame {f}")
 
 
+@pytest.mark.parametrize("name", __import__("conftest").big_golden_names())
+def test_c_oracle_fused_matches_reference_at_full_size(name):
+    """BASELINE configs[2] (8 cameras x 4 persons x 133 joints, 2 frames) and configs[3] (16 x 8 x 133, 1 frame):
+    the C oracle against what the REAL reference emitted (tests/golden/make_golden_big.py)."""
+    from conftest import BigGolden
+    g = BigGolden(name)
+    p = g.params
+    pout = max(1, max(c[0].shape[0] for c in g.con))
+    r = c_oracle.fused(g.kpts, g.scores, g.counts, g.K, g.R, g.t, p, Pout=pout, keypoint_num=p["keypoint_num"])
+    for f in range(g.F):
+        n = g.con[f][0].shape[0]
+        assert r["nout"][f] == n
+        assert r["ncand"][f] == g.tri_ps[f].shape[0]
+        _check((r["points"][f, :n], r["kscores"][f, :n], r["pscores"][f, :n]), g.con[f], f"{name} frame {f}")
+
+
 def test_fused_threads_agree():
     rig = synth.ring_rig(6)
     d = synth.make_frames(rig, 24, 2, 17, seed=5, low_score_frac=0.1, drop_prob=0.1)
