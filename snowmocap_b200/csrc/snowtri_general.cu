@@ -1,5 +1,6 @@
 // Host side of the streaming general path (snowtri_general.cuh): scratch management, frame chunking, launches.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "snowtri_internal.h"
@@ -27,7 +28,14 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
     a.kpts = g.kpts; a.scores = g.scores; a.out = g.out; a.pscores = g.pscores; a.nout = g.nout;
     a.kcount = g.kcount; a.desc = desc; a.memb2 = memb2;
     a.F = g.F; a.P = g.P; a.J = g.J; a.Jout = g.Jout; a.Pout = g.Pout; a.ncand = g.ncand;
-    a.Gw = 32 / g.Pout < 1 ? 1 : 32 / g.Pout;
+    // frames per tile: about a thousand (row, joint) items (few idle lanes in the last step), at most 32 rows
+    {
+        const int rows = g.Pout / 2 > 0 ? g.Pout / 2 : 1;
+        int gw = (1024 + rows * g.Jout - 1) / (rows * g.Jout);
+        const int cap = 32 / g.Pout < 1 ? 1 : 32 / g.Pout;
+        a.Gw = gw < 1 ? 1 : (gw > cap ? cap : gw);
+    }
+    a.tile_counter = g.tile_counter;
     a.kst_f = h->prm.kst_f;
     const double inv = h->prm.dthr > 0.0 ? 1.0 / h->prm.dthr : (double)INFINITY;
     a.inv_dthr = (float)inv;
@@ -61,14 +69,17 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
                     a.E[9 * e + 3 * i + j2] = (double)(-v);
                 }
         }
-    auto kern = mfuse_kernel<C, NT, MINB>;
+    // small rigs: everything unrolled fits the instruction cache; from 6 cameras on the rolled form (SNOWTRI_MF_ROLLED=0/1 overrides)
+    const char* env = getenv("SNOWTRI_MF_ROLLED");
+    const bool rolled = env ? atoi(env) != 0 : C >= 6;
+    auto kern = rolled ? mfuse_kernel<C, NT, MINB, true> : mfuse_kernel<C, NT, MINB, false>;
     const size_t smem = (size_t)(NT / 32) * mfuse_warp_bytes<C>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "mfuse_kernel attribute: %s", cudaGetErrorString(e));
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
     if (occ < 1) occ = 1;
-    int grid = h->sm_count * occ;  // one contiguous frame range per warp; a short batch uses fewer CTAs
+    int grid = h->sm_count * occ;  // persistent warps fetch tiles from a counter; a short batch uses fewer CTAs
     const long long tiles = ((long long)g.F + a.Gw - 1) / a.Gw;
     if ((long long)grid * (NT / 32) > tiles) grid = (int)((tiles + NT / 32 - 1) / (NT / 32));
     if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
@@ -130,7 +141,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     if (fc_max > F) fc_max = F;
     if (h->tune_G > 0 && fc_max > h->tune_G) fc_max = h->tune_G;  // tests: force several chunks
     const size_t need = align16(fc_max * nc) * 2 + align16(fc_max * nc * 24) + align16(fc_max * nc * 4) * 4 +
-                        align16(fc_max * nc * 8) + align16(fc_max * 4) + align16((size_t)fc_max * Pout * 16) +
+                        align16(fc_max * nc * 8) + align16(fc_max * 4) + align16((size_t)fc_max * Pout * 16) + 16 +
                         (match_glob ? align16((size_t)fc_max * R * 16) : 0) + 256;
     if (h->gen_scratch_bytes < need) {
         if (h->gen_scratch) cudaFree(h->gen_scratch);
@@ -150,6 +161,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     a.cstart = (int*)take(fc_max * nc * 4);
     a.cn = (int*)take(fc_max * nc * 4);
     a.kcount = (int*)take(fc_max * 4);
+    a.tile_counter = fuse2 ? (int*)take(16) : nullptr;
     a.keep = take(fc_max * nc);
     a.ab = take(fc_max * nc);
     a.memb2 = fuse2 ? memb2 : nullptr;   // the clustering kernels then also decode the members and describe the rows
@@ -178,10 +190,10 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
             // frames that do not fit in shared memory)
             const int mitems = a.npairs * tpp * tpp;  // (camera pair, 4 x 4 person tile) per frame
             if (match_smem) {
-                // warps per CTA: as many as divide the frame's items evenly (<= 8: two CTAs per SM)
-                int nw = 8;
+                // warps per CTA: as many as divide the frame's items evenly (<= 7: two CTAs per SM at 146 registers)
+                int nw = 7;
                 double best = 0.0;
-                for (int w = 8; w >= 4; --w) {
+                for (int w = 7; w >= 4; --w) {
                     const double eff = (double)mitems / (double)(((mitems + w - 1) / w) * w);
                     if (eff > best + 1e-9) { best = eff; nw = w; }
                 }

@@ -56,6 +56,7 @@ struct GenArgs {
     int* kcount;          // (F)
     uint2* memb2;         // (F,ncand) decoded members, written by the clustering kernels when non-null
     GenDesc* desc;        // (F,Pout) row descriptors, written by the clustering kernels when non-null
+    int* tile_counter;    // work counter of the fuse kernel that follows, zeroed by the clustering kernels when non-null
 };
 
 constexpr int kGenWarps = 8;  // warps per CTA of K1/K3/K4
@@ -316,6 +317,7 @@ __global__ void __launch_bounds__(256) gen_cluster_block_kernel(const __grid_con
     const int K = cluster_block<256>(a.ncand, a.keep + o, a.klist + o, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o,
                                      a.cn + o, wtmp, a.tol2, a.prm.num_tol);
     if (threadIdx.x == 0) a.kcount[f] = K;
+    if (a.tile_counter && blockIdx.x == 0 && threadIdx.x == 0) *a.tile_counter = 0;
     if (a.memb2) {  // cluster_block ends with a barrier: the lists are visible to the whole CTA
         __syncthreads();
         gen_describe(a, f, K, threadIdx.x, 256);
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const 
     const int K = cluster_warp(nk, kl, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o, a.cn + o, a.tol2,
                                a.prm.num_tol, lane);
     if (lane == 0) a.kcount[f] = K;
+    if (a.tile_counter && f == 0 && lane == 0) *a.tile_counter = 0;
     if (a.memb2) {
         __syncwarp();
         gen_describe(a, f, K, lane, 32);

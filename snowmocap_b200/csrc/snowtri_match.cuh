@@ -14,8 +14,8 @@
 //     the per-main-ray part of the triple product (d x hm) hoisted out of the 4 secondary persons;
 //   * the gate needs no cross product:  d.(hm x hs) = hs.(d x hm)  and  |hm x hs|^2 = |hm|^2 |hs|^2 - (hm.hs)^2,
 //     10 FMA-class operations per evaluation;
-//   * 16 running sums per lane in registers (static indices only: nothing in local memory), ONE butterfly reduction
-//     per tile (16 + 4x5 shuffles) instead of two 5-step reductions per candidate;
+//   * 2 x 16 running sums per lane in registers (static indices only: nothing in local memory), two butterfly
+//     reductions per tile (2 x 16 shuffles) instead of two 5-step reductions per candidate;
 //   * the decision, its float64 re-evaluation when the float32 sum is closer to the threshold than its error bound,
 //     and the float64 centre of the kept candidates happen in the same warp, so the keep byte and the centre are the
 //     only things written.
@@ -83,16 +83,24 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
     bool kept = present;
 
     if (!a.all_kept && nm > 0 && ns > 0) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
-        float sum[kTile * kTile], err[kTile];
+        // Two running sums per candidate, a LOWER and an UPPER bound of its float64 score sum.  A joint's score is
+        // c/dist and the float32 ray distance is good to kDistDelta metres, so with t = kDistDelta/dist the true score
+        // lies in [w/(1+t), w/(1-t)] which contains [w(1-t), w(1+2t)] for t <= 1/2 (beyond that the upper bound is
+        // +inf).  A joint whose gate sits inside its guard band counts in the upper bound only.  One-sided bounds
+        // matter: scores are heavy-tailed (rays that happen to pass within 0.01 mm score 80 +- 80), which blows up
+        // a symmetric error bar -- with it every fourth correctly matched candidate went to the float64 path
+        // (profiles/r2a) -- but not the lower bound, and "kept" only needs the lower bound above the threshold.
+        float lo[kTile * kTile], hi[kTile * kTile];
 #pragma unroll
-        for (int i = 0; i < kTile * kTile; ++i) sum[i] = 0.f;
-#pragma unroll
-        for (int i = 0; i < kTile; ++i) err[i] = 0.f;
+        for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
         V3<float> d;
         d.x = (float)(camD[12 * sc + 9] - camD[12 * mc + 9]);
         d.y = (float)(camD[12 * sc + 10] - camD[12 * mc + 10]);
         d.z = (float)(camD[12 * sc + 11] - camD[12 * mc + 11]);
         const float dthr2 = (float)(a.prm.dthr * a.prm.dthr);
+        // relative half-width of the gate's guard band on squared quantities: float32 arithmetic (kGateGuard) or the
+        // distance error bound relative to a small threshold, whichever is wider
+        const float guard2 = 2.f * fmaxf(kGateGuard, 4.f * kDistDelta / (float)a.prm.dthr);
         const float4* rm = rays + (size_t)(mc * P + pm0) * J;
         const float4* rs = rays + (size_t)(sc * P + ps0) * J;
         const float* qm = scs + (size_t)(mc * P + pm0) * J;
@@ -130,36 +138,30 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
                     const float nn = fmaf(m[i].w, s[k].w, -(B * B));
                     const float dn2 = dn * dn, lim = dthr2 * nn;
                     const bool pass = !lowm && !(dn2 > lim);  // dist > dthr is gated (strict); NaN is not (Q8/Q9)
-                    const bool near = !lowm && fabsf(dn2 - lim) < (2.f * kGateGuard) * lim;
+                    const bool near = !lowm && fabsf(dn2 - lim) < guard2 * lim;
                     if (__any_sync(kFull, pass || near)) {
                         const float rd = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);  // sqrt(n.n)/|d.n| = 1/dist
                         const float w = (sm[i] + ss[k]) * 0.0005f * rd;
-                        // error bound in units of kDistDelta: score/dist, plus the whole score of a joint whose
-                        // gate could flip (shared by the 4 candidates of a main person: a larger bound is still a bound)
-                        if (pass) {
-                            sum[i * kTile + k] += w;
-                            err[i] = fmaf(w, rd, err[i]);
-                        }
-                        if (near) err[i] = fmaf(w, 1.0f / kDistDelta, err[i]);
+                        const float t = kDistDelta * rd, we = w * t;
+                        if (pass && !near) lo[i * kTile + k] += fmaxf(w - we, 0.f);
+                        if (pass || near) hi[i * kTile + k] += t <= 0.5f ? fmaf(2.f, we, w) : INFINITY;
                     }
                 }
             }
         }
-        const float tot = reduce16(sum, lane);
-#pragma unroll
-        for (int i = 0; i < kTile; ++i) err[i] = warp_sum(err[i]);
-        const float e = ci == 0 ? err[0] : (ci == 1 ? err[1] : (ci == 2 ? err[2] : err[3]));
-        // mean < ast  <=>  sum < ast*J; the float32 sum decides unless it sits on the threshold
-        const double thrJ = a.prm.ast * (double)J, gap = fabs((double)tot - thrJ);
-        kept = present && !((double)tot < thrJ);  // NaN mean is kept (Q9)
-        const double slack = (double)kDistDelta * (double)e + 4e-5 * fabs((double)tot);
-        unsigned redo = __ballot_sync(kFull, present && !(lane & 1) && !(gap > slack));
-        while (redo) {  // discrete decision: the whole warp redoes this candidate in float64 from the raw inputs
+        const float lo_tot = reduce16(lo, lane), hi_tot = reduce16(hi, lane);
+        // mean < ast  <=>  sum < ast*J.  4e-5: float32 rounding of the weights (|hm x hs|^2 from the Gram form) and
+        // of the 133-term sums, relative.  Anything else (also NaN) is decided in float64 from the raw inputs.
+        const double thrJ = a.prm.ast * (double)J;
+        const bool surely_kept = (double)lo_tot * (1.0 - 4e-5) >= thrJ, surely_not = (double)hi_tot * (1.0 + 4e-5) < thrJ;
+        kept = present && surely_kept;
+        unsigned redo = __ballot_sync(kFull, present && !(lane & 1) && !surely_kept && !surely_not);
+        while (redo) {  // discrete decision: the whole warp redoes this candidate in float64
             const int l = __ffs(redo) - 1;
             redo &= redo - 1;
             const int cc = l >> 1;
             const double mean = gen_candidate_mean_f64(a, camD, kf, sf, mc, pm0 + (cc >> 2), sc, ps0 + (cc & 3), lane);
-            if ((lane >> 1) == cc) kept = !(mean < a.prm.ast);
+            if ((lane >> 1) == cc) kept = !(mean < a.prm.ast);  // NaN mean is kept (Q9)
         }
     }
 
@@ -209,7 +211,7 @@ struct MatchTables {
 // Frames whose rays fit in shared memory (20 bytes per ray): one CTA per frame builds them once and its warps walk the
 // (camera pair, tile) items out of shared memory.  Two CTAs per SM: one CTA's ray build (global loads) and decisions
 // overlap the other's arithmetic.
-__global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
+__global__ void __launch_bounds__(224, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     MatchTables tb(smem, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;

@@ -32,6 +32,7 @@ struct MFArgs {
     const int* kcount;     // (F) clusters per frame
     const GenDesc* desc;   // (F,Pout)
     const uint2* memb2;    // (F,ncand)
+    int* tile_counter;     // next tile of Gw frames (zero at launch)
     int F, P, J, Jout, Pout, Gw, ncand;
     float kst_f, inv_dthr, guard_w;
     double inv_dthr64;
@@ -105,10 +106,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int C>
 __host__ __device__ constexpr size_t mfuse_warp_bytes() { return 32 * 24 + 32 * 33 * 4 + (size_t)C * 32 * 12; }
 
-template <int C, int NT, int MINB>
+template <int C, int NT, int MINB, bool ROLLED>
 __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__ MFArgs<C> a) {
-    constexpr int NW = NT / 32;
-    constexpr unsigned ALLC = (1u << C) - 1u;
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int J = a.J, Jout = a.Jout, Pout = a.Pout, P = a.P, Gw = a.Gw;
@@ -123,12 +122,17 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
 
     const float2* kp2 = reinterpret_cast<const float2*>(a.kpts);
     const size_t R = (size_t)C * P * J;
-    const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
-    const int fa = (int)((long long)a.F * gwarp / nwarps), fb = (int)((long long)a.F * (gwarp + 1) / nwarps);
     const unsigned lt = (1u << lane) - 1u;
 
-    for (int f0 = fa; f0 < fb; f0 += Gw) {
-        const int Gc = min(Gw, fb - f0);
+    // Tiles of Gw frames are handed out through a counter (zeroed by the clustering kernel that runs before this one):
+    // rows per frame vary, and with static frame ranges the average SM was idle for the last fifth of the launch.
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(a.tile_counter, 1);
+        tile = __shfl_sync(kFull, tile, 0);
+        if ((long long)tile * Gw >= a.F) break;
+        const int f0 = tile * Gw;
+        const int Gc = min(Gw, a.F - f0);
         // ---- rows of the tile: the clusters that have an output slot, compacted in (frame, slot) order ----------
         int nrows;
         {
@@ -183,8 +187,10 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
         int row, j;
         locate(lane, row, j);
         stage_inputs(row, j);
-        float acc = 0.f;  // this lane's share of the person score of row `racc`
-        int racc = row;
+        // this lane's share of the person score of row `racc`: the items of one row a lane meets are 32 joints apart, so
+        // they all belong to column j & 31 of the row -- the sum does not depend on where the row sits in the tile
+        float acc = 0.f;
+        int racc = row, cacc = j & 31;
 
         for (int q0 = 0; q0 < nitems; q0 += 32) {
             const bool live = q0 + lane < nitems;
@@ -194,7 +200,6 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
             V3<float> h[C];
             float A[C], sc[C];
             double ud[C], vd[C];
-            unsigned on = 0;
             cp_async_wait_all();
 #pragma unroll
             for (int c = 0; c < C; ++c) {
@@ -205,7 +210,6 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
                 ud[c] = (double)p2.x;
                 vd[c] = (double)p2.y;
                 const bool here = ((unsigned)(obs >> (8 * c)) & 0xffu) != 0xffu;
-                on |= (here ? 1u : 0u) << c;
                 // a score below the keypoint threshold (or an absent camera) kills every pair of the camera: poison it
                 // so that max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
                 sc[c] = (!here || s1 < a.kst_f) ? -1e30f : s1;
@@ -221,52 +225,84 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
             const float* sfj = a.scores + fo * R + j;
             const uint2* mb = a.memb2 + fo * a.ncand + (start & 0x7fffffff);
             if (__all_sync(kFull, clique)) {
-                float S = 0.f, Xm = 0.f, Ym = 0.f, Zm = 0.f, al[C];
+                // The pairs (x, y), x < y.  ROLLED: x in a rolled loop, y unrolled -- all 28 pairs of 8 cameras unrolled
+                // are 25 KB of straight-line code per item and 40 % of the warp stalls were instruction fetches
+                // (profiles/r2a); rolled, the body is 7 pair solves, camera x's registers are picked by a switch on
+                // the warp-uniform x and the pair constants are indexed at run time.  An absent camera (sub-clique)
+                // or a low score contributes exactly zero through the score test.
+                float S = 0.f, Xm = 0.f, Ym = 0.f, Zm = 0.f, X = 0.f, Y = 0.f, Z = 0.f, al[C];
                 float margin = INFINITY;  // smallest |1/dist - 1/dthr| over the pairs
 #pragma unroll
                 for (int c = 0; c < C; ++c) al[c] = 0.f;
-                auto pair = [&](auto xc, auto yc) {
-                    constexpr int x = decltype(xc)::value, y = decltype(yc)::value;
-                    constexpr int e = pair_index(C, x, y);
+                // one pair: camera x's values in scalars, camera y's by static index, pair constants at index e
+                auto pair = [&](const V3<float>& hx, float Ax, float sx, double udx, double vdx, float& alx, int y, int e) {
                     V3<float> d;
                     d.x = a.pdc[e * 8]; d.y = a.pdc[e * 8 + 1]; d.z = a.pdc[e * 8 + 2];
-                    const PairSolN<float> s = pair_solve_n(h[x], A[x], h[y], A[y], d);
+                    const PairSolN<float> s = pair_solve_n(hx, Ax, h[y], A[y], d);
                     // d.(hm x hs) in float64 from the pixel coordinates: l = E [uy vy 1]^T, dn = [ux vx 1] l
-                    const double l0 = fma(a.E[9 * e + 0], ud[y], fma(a.E[9 * e + 1], vd[y], a.E[9 * e + 2]));
-                    const double l1 = fma(a.E[9 * e + 3], ud[y], fma(a.E[9 * e + 4], vd[y], a.E[9 * e + 5]));
-                    const double l2 = fma(a.E[9 * e + 6], ud[y], fma(a.E[9 * e + 7], vd[y], a.E[9 * e + 8]));
-                    const float dn = (float)fma(l0, ud[x], fma(l1, vd[x], l2));
+                    const double* E = a.E + 9 * e;
+                    const double l0 = fma(E[0], ud[y], fma(E[1], vd[y], E[2]));
+                    const double l1 = fma(E[3], ud[y], fma(E[4], vd[y], E[5]));
+                    const double l2 = fma(E[6], ud[y], fma(E[7], vd[y], E[8]));
+                    const float dn = (float)fma(l0, udx, fma(l1, vdx, l2));
                     const float r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
                     const float rd = r * s.det;                   // 1/dist
                     margin = fminf(margin, fabsf(rd - a.inv_dthr));
-                    float gq = fmaxf(sc[x] + sc[y], 0.f) * r;
-                    if (rd < a.inv_dthr) gq = 0.f;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
+                    // score: zero when a score is below kst (poisoned, also absent cameras) or dist > dthr
+                    // (strict; a NaN distance is not gated, Q8/Q9)
+                    const float ssum = sx + sc[y];
+                    const float gq = (ssum > 0.f && !(rd < a.inv_dthr)) ? ssum * r : 0.f;
                     const float w = gq * s.det;
                     S += w;
-                    al[x] = fmaf(gq, s.n0, al[x]);
+                    alx = fmaf(gq, s.n0, alx);
                     al[y] = fmaf(-gq, s.n1, al[y]);
                     Xm = fmaf(w, a.pdc[e * 8 + 4], Xm);
                     Ym = fmaf(w, a.pdc[e * 8 + 5], Ym);
                     Zm = fmaf(w, a.pdc[e * 8 + 6], Zm);
                 };
-                if (__all_sync(kFull, on == ALLC)) {  // every lane's person is seen by every camera: branch-free
-                    static_for_pairs<C>([&](auto xc, auto yc) { pair(xc, yc); });
+                if constexpr (ROLLED) {
+#pragma unroll 1
+                    for (int x = 0; x < C - 1; ++x) {
+                        V3<float> hx = h[0];
+                        float Ax = A[0], sx = sc[0], alx = al[0];
+                        double udx = ud[0], vdx = vd[0];
+                        switch (x) {
+#define MF_PICK(c_)                                                                                     \
+    case c_:                                                                                            \
+        if constexpr (c_ < C) {                                                                         \
+            hx = h[c_]; Ax = A[c_]; sx = sc[c_]; alx = al[c_]; udx = ud[c_]; vdx = vd[c_];              \
+        }                                                                                               \
+        break;
+                            MF_PICK(1) MF_PICK(2) MF_PICK(3) MF_PICK(4) MF_PICK(5) MF_PICK(6) MF_PICK(7)
+#undef MF_PICK
+                            default: break;
+                        }
+                        const int ebase = x * C - x * (x + 1) / 2 - x - 1;  // pair_index(C, x, y) = ebase + y
+#pragma unroll
+                        for (int y = 1; y < C; ++y)
+                            if (y > x) pair(hx, Ax, sx, udx, vdx, alx, y, ebase + y);
+                        X = fmaf(alx, hx.x, X);  // camera x has met every partner: its alpha is complete
+                        Y = fmaf(alx, hx.y, Y);
+                        Z = fmaf(alx, hx.z, Z);
+                    }
+                    X = fmaf(al[C - 1], h[C - 1].x, X);
+                    Y = fmaf(al[C - 1], h[C - 1].y, Y);
+                    Z = fmaf(al[C - 1], h[C - 1].z, Z);
                 } else {
                     static_for_pairs<C>([&](auto xc, auto yc) {
-                        constexpr unsigned both = (1u << decltype(xc)::value) | (1u << decltype(yc)::value);
-                        if ((on & both) == both) pair(xc, yc);
+                        constexpr int x = decltype(xc)::value, y = decltype(yc)::value;
+                        pair(h[x], A[x], sc[x], ud[x], vd[x], al[x], y, pair_index(C, x, y));
                     });
-                }
-                if (margin < a.guard_w) {  // a float32 distance within the guard band of dthr: decide in float64
-                    o = mf_item_members<C>(a, kfj, sfj, mb, n);
-                } else if (S != 0.f) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
-                    float X = 0.f, Y = 0.f, Z = 0.f;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
                         X = fmaf(al[c], h[c].x, X);
                         Y = fmaf(al[c], h[c].y, Y);
                         Z = fmaf(al[c], h[c].z, Z);
                     }
+                }
+                if (margin < a.guard_w) {  // a float32 distance within the guard band of dthr: decide in float64
+                    o = mf_item_members<C>(a, kfj, sfj, mb, n);
+                } else if (S != 0.f) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
                     const float rS = rcp_fast(S);
                     o.x = fmaf(0.5f, X, Xm) * rS;
                     o.y = fmaf(0.5f, Y, Ym) * rS;
@@ -279,16 +315,17 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
             if (live) {
                 reinterpret_cast<float4*>(a.out)[(fo * Pout + (gk & 0xff)) * Jout + j] = o;
                 if (row != racc) {
-                    part[racc * 33 + lane] = acc;
+                    part[racc * 33 + cacc] = acc;
                     acc = 0.f;
                     racc = row;
+                    cacc = j & 31;
                 }
                 acc += o.w;
             }
             row = rown;
             j = jn;
         }
-        if (lane < nitems) part[racc * 33 + lane] = acc;
+        if (lane < nitems) part[racc * 33 + cacc] = acc;
         __syncwarp();
         // ---- person score = mean keypoint score (reference :150): lane r adds up the 32 columns of row r ----------
         if (lane < nrows) {

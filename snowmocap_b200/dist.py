@@ -15,6 +15,18 @@ def shard_range(F, rank, world):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def shard_cyclic(F, rank, world, nchunks):
+    """Block-cyclic frame sharding for a gather that overlaps the compute: the clip is cut into ``nchunks * world``
+    equal chunks and chunk ``m`` goes to rank ``m % world`` as its ``m // world``-th piece.  Returns the list of
+    global frame ranges [(lo, hi), ...] of ``rank``, in processing order; ``F`` must be a multiple of
+    ``nchunks * world``.  All-gathering piece k of every rank yields the global frames
+    [k*world*c, (k+1)*world*c) in order (c = F / (nchunks*world)), so the gathered clip needs no reordering."""
+    if F % (nchunks * world):
+        raise ValueError(f"F={F} is not a multiple of nchunks*world={nchunks * world}")
+    c = F // (nchunks * world)
+    return [((k * world + rank) * c, (k * world + rank + 1) * c) for k in range(nchunks)]
+
+
 def all_gather_frames(local, F, group=None):
     """All-gather per-rank frame blocks (uneven allowed) into the full (F, ...) tensor on every rank."""
     world = dist.get_world_size(group)
@@ -98,3 +110,32 @@ def all_gather_frames_native(engine, local, world, stream=None):
         _lib.check(engine._lib.snowtri_allgather(engine._h, local.data_ptr(), out.data_ptr(),
                                                  local.numel() * local.element_size(), None, st), engine._h)
     return out
+
+
+def triangulate_cyclic_overlapped(engine, pieces, local, full, world, comm_stream, Pout=None, keypoint_num=None):
+    """Block-cyclic sharded run with the final all-gather of the 3D joints overlapped with the compute (north_star:
+    "NCCL over NVLink appears only as a final all-gather of 3D joints"): piece k of this rank (``shard_cyclic``) is
+    triangulated on the current stream, then its ``out`` / ``pscores`` / ``nout`` blocks are all-gathered with
+    ``snowtri_allgather`` on ``comm_stream`` while piece k+1 is being computed.
+
+      pieces  [(kpts_k, scores_k, counts_k or None), ...] device tensors of this rank, c frames each
+      local   [dict(out, pscores, nout), ...] per-piece result buffers of this rank
+      full    dict(out (F,Pout,Jout,4), pscores (F,Pout), nout (F,)) -- the gathered clip, frames in global order
+
+    ``init_native_comm(engine)`` first.  The current stream waits for the last gather before returning."""
+    from . import _lib
+    main = torch.cuda.current_stream(engine.device)
+    c = pieces[0][1].shape[0] if pieces else 0
+    for k, (kp, sc, cn) in enumerate(pieces):
+        engine.run(kp, sc, cn, Pout=Pout, keypoint_num=keypoint_num, out=local[k])
+        ev = torch.cuda.Event()
+        ev.record(main)
+        comm_stream.wait_event(ev)
+        lo = k * world * c
+        with torch.cuda.device(engine.device):
+            for name in ("out", "pscores", "nout"):
+                src, dst = local[k][name], full[name][lo:lo + world * c]
+                _lib.check(engine._lib.snowtri_allgather(engine._h, src.data_ptr(), dst.data_ptr(),
+                                                         src.numel() * src.element_size(), None, comm_stream.cuda_stream),
+                           engine._h)
+    main.wait_stream(comm_stream)

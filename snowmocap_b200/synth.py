@@ -141,3 +141,44 @@ def make_frames_torch(rig, F, P, J, seed=1234, device="cuda", noise_px=0.5, chun
         kpts[f0:f0 + n] = uv.to(torch.float32)
         scores[f0:f0 + n] = torch.rand((n, C, P, J), generator=gen, device=device) * 0.4 + 0.6
     return kpts, scores
+
+
+def frames_block(C, P, J):
+    """Frames per independently seeded block of ``make_frames_torch_range`` (a function of the shape only, so that
+    every rank of a sharded run generates the same frames as the single-GPU run)."""
+    return int(max(16, min(1024, (1 << 24) // max(1, C * P * J))))
+
+
+def make_frames_torch_range(rig, f_lo, f_hi, P, J, seed=1234, device="cuda", noise_px=0.5):
+    """Frames [f_lo, f_hi) of the endless synthetic clip ``seed``: same distribution as ``make_frames_torch``, but a
+    frame's content depends only on (seed, global frame index), not on how the clip is cut into shards or batches.
+    Returns (kpts (n,C,P,J,2) f32, scores (n,C,P,J) f32)."""
+    import torch
+    C = rig.C
+    B = frames_block(C, P, J)
+    Rt = torch.as_tensor(rig.R, device=device).transpose(1, 2).contiguous()
+    K = torch.as_tensor(rig.K, device=device)
+    t = torch.as_tensor(rig.t, device=device)
+    n_tot = max(0, f_hi - f_lo)
+    kpts = torch.empty((n_tot, C, P, J, 2), dtype=torch.float32, device=device)
+    scores = torch.empty((n_tot, C, P, J), dtype=torch.float32, device=device)
+    gen = torch.Generator(device=device)
+    for b in range(f_lo // B, (f_hi + B - 1) // B if n_tot else 0):
+        gen.manual_seed((seed * 1000003 + b) & 0x7FFFFFFFFFFF)
+        centre = torch.zeros((B, P, 1, 3), dtype=torch.float64, device=device)
+        centre[..., :2] = torch.rand((B, P, 1, 2), generator=gen, dtype=torch.float64, device=device) * 4 - 2
+        body = torch.rand((B, P, J, 3), generator=gen, dtype=torch.float64, device=device)
+        body[..., :2] = body[..., :2] * 0.8 - 0.4
+        body[..., 2] *= 1.8
+        X = centre + body
+        Xc = torch.einsum("cij,ncpqj->ncpqi", Rt, X[:, None] - t[None, :, None, None, :])
+        uvw = torch.einsum("cij,ncpqj->ncpqi", K, Xc)
+        uv = uvw[..., :2] / uvw[..., 2:3]
+        uv = uv + noise_px * torch.randn(uv.shape, generator=gen, dtype=torch.float64, device=device)
+        perm = torch.argsort(torch.rand((B, C, P), generator=gen, device=device), dim=-1)
+        uv = torch.gather(uv, 2, perm[..., None, None].expand(-1, -1, -1, J, 2)).to(torch.float32)
+        sc = torch.rand((B, C, P, J), generator=gen, device=device) * 0.4 + 0.6
+        lo, hi = max(f_lo, b * B), min(f_hi, (b + 1) * B)
+        kpts[lo - f_lo:hi - f_lo] = uv[lo - b * B:hi - b * B]
+        scores[lo - f_lo:hi - f_lo] = sc[lo - b * B:hi - b * B]
+    return kpts, scores
