@@ -69,9 +69,9 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
                     a.E[9 * e + 3 * i + j2] = (double)(-v);
                 }
         }
-    // small rigs: everything unrolled fits the instruction cache; from 6 cameras on the rolled form (SNOWTRI_MF_ROLLED=0/1 overrides)
+    // pair loop fully unrolled (default) or with the first camera of a pair in a rolled loop (SNOWTRI_MF_ROLLED=1)
     const char* env = getenv("SNOWTRI_MF_ROLLED");
-    const bool rolled = env ? atoi(env) != 0 : C >= 6;
+    const bool rolled = env ? atoi(env) != 0 : false;   // measured at 8 cameras: unrolled 0.82 ms, rolled 1.15 ms (profiles/r2b)
     auto kern = rolled ? mfuse_kernel<C, NT, MINB, true> : mfuse_kernel<C, NT, MINB, false>;
     const size_t smem = (size_t)(NT / 32) * mfuse_warp_bytes<C>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));

@@ -21,8 +21,8 @@
 //     only things written.
 // Discrete decisions stay exact: same error-bound logic as gen_keep_item (kDistDelta, guard band on the gate), and
 // anything that turns the float32 sum into NaN (non-finite inputs, parallel rays) falls into the float64 path.
-// Requires dthr > 0 (the sign trick for low scores needs a positive gate limit); the host keeps the first-generation
-// kernels for dthr <= 0 and for the all-float64 mode.
+// Requires dthr > 0 (the gate is tested on 1/dist against 1/dthr); the host keeps the first-generation kernels for
+// dthr <= 0 and for the all-float64 mode.
 #pragma once
 #include "snowtri_general.cuh"
 
@@ -85,8 +85,9 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
     if (!a.all_kept && nm > 0 && ns > 0) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
         // Two running sums per candidate, a LOWER and an UPPER bound of its float64 score sum.  A joint's score is
         // c/dist and the float32 ray distance is good to kDistDelta metres, so with t = kDistDelta/dist the true score
-        // lies in [w/(1+t), w/(1-t)] which contains [w(1-t), w(1+2t)] for t <= 1/2 (beyond that the upper bound is
-        // +inf).  A joint whose gate sits inside its guard band counts in the upper bound only.  One-sided bounds
+        // lies in [w/(1+t), w/(1-t)] which contains [w(1-t), w(1+2t)] for t <= 1/2 (beyond that the joint adds nothing
+        // to the lower bound and +inf to the upper).  A joint whose gate sits inside its guard band counts in the
+        // upper bound only.  One-sided bounds
         // matter: scores are heavy-tailed (rays that happen to pass within 0.01 mm score 80 +- 80), which blows up
         // a symmetric error bar -- with it every fourth correctly matched candidate went to the float64 path
         // (profiles/r2a) -- but not the lower bound, and "kept" only needs the lower bound above the threshold.
@@ -97,15 +98,16 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
         d.x = (float)(camD[12 * sc + 9] - camD[12 * mc + 9]);
         d.y = (float)(camD[12 * sc + 10] - camD[12 * mc + 10]);
         d.z = (float)(camD[12 * sc + 11] - camD[12 * mc + 11]);
-        const float dthr2 = (float)(a.prm.dthr * a.prm.dthr);
-        // relative half-width of the gate's guard band on squared quantities: float32 arithmetic (kGateGuard) or the
-        // distance error bound relative to a small threshold, whichever is wider
-        const float guard2 = 2.f * fmaxf(kGateGuard, 4.f * kDistDelta / (float)a.prm.dthr);
+        // gate on 1/dist, pulled in / pushed out by the guard band: a joint surely passes at 1/dist >= r_sure, may pass
+        // at 1/dist >= r_maybe.  The band is the float32 error of the distance (kGateGuard, relative) or the distance
+        // error bound relative to a small threshold, whichever is wider.
+        const float guard = fmaxf(kGateGuard, 4.f * kDistDelta / (float)a.prm.dthr);
+        const float r_sure = (float)(1.0 / a.prm.dthr) * (1.f + guard), r_maybe = (float)(1.0 / a.prm.dthr) * (1.f - guard);
         const float4* rm = rays + (size_t)(mc * P + pm0) * J;
         const float4* rs = rays + (size_t)(sc * P + ps0) * J;
         const float* qm = scs + (size_t)(mc * P + pm0) * J;
         const float* qs = scs + (size_t)(sc * P + ps0) * J;
-        for (int j0 = 0; j0 < J; j0 += 32) {  // every lane stays in the loop: the slow path is behind a vote
+        for (int j0 = 0; j0 < J; j0 += 32) {
             const bool valid = j0 + lane < J;
             const int j = valid ? j0 + lane : J - 1;
             float4 m[kTile], s[kTile];
@@ -123,9 +125,21 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
                 ss[k] = qs[(size_t)r * J + j];
                 if (k >= ns) s[k].w = -1.f;
             }
+            // a secondary ray with a low score (it carries -|hs|^2) or beyond the count is gated through its limits
+            float lim_sure[kTile], lim_maybe[kTile];
+#pragma unroll
+            for (int k = 0; k < kTile; ++k) {
+                const bool oks = !(s[k].w < 0.f);
+                lim_sure[k] = oks ? r_sure : INFINITY;
+                lim_maybe[k] = oks ? r_maybe : INFINITY;
+                s[k].w = fabsf(s[k].w);
+            }
+            // Straight-line, predicated: a vote around the score arithmetic does not pay -- with 32 joints per warp
+            // some lane of a wrongly matched pair passes the 5 cm gate two times out of three (measured: the voted
+            // branch ran for 65 % of the evaluations and serialised their dependency chains, profiles/r2b).
 #pragma unroll
             for (int i = 0; i < kTile; ++i) {
-                const bool lowm = !valid || i >= nm || m[i].w < 0.f;
+                const bool okm = valid && i < nm && !(m[i].w < 0.f);
                 V3<float> e;  // d x hm:  d.(hm x hs) = hs.(d x hm)
                 e.x = fmaf(d.y, m[i].z, -(d.z * m[i].y));
                 e.y = fmaf(d.z, m[i].x, -(d.x * m[i].z));
@@ -134,22 +148,19 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
                 for (int k = 0; k < kTile; ++k) {
                     const float B = fmaf(m[i].x, s[k].x, fmaf(m[i].y, s[k].y, m[i].z * s[k].z));
                     const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
-                    // |hm x hs|^2; a secondary ray with a low score carries -|hs|^2: nn < 0, lim < 0 <= dn2, gated
-                    const float nn = fmaf(m[i].w, s[k].w, -(B * B));
-                    const float dn2 = dn * dn, lim = dthr2 * nn;
-                    const bool pass = !lowm && !(dn2 > lim);  // dist > dthr is gated (strict); NaN is not (Q8/Q9)
-                    const bool near = !lowm && fabsf(dn2 - lim) < guard2 * lim;
-                    if (__any_sync(kFull, pass || near)) {
-                        const float rd = nn * rsqrt_fast(nn) * rsqrt_fast(dn2);  // sqrt(n.n)/|d.n| = 1/dist
-                        const float w = (sm[i] + ss[k]) * 0.0005f * rd;
-                        const float t = kDistDelta * rd, we = w * t;
-                        if (pass && !near) lo[i * kTile + k] += fmaxf(w - we, 0.f);
-                        if (pass || near) hi[i * kTile + k] += t <= 0.5f ? fmaf(2.f, we, w) : INFINITY;
-                    }
+                    const float nn = fmaf(m[i].w, s[k].w, -(B * B));  // |hm x hs|^2
+                    const float rd = nn * rsqrt_fast(nn * (dn * dn));  // sqrt(n.n)/|d.n| = 1/dist
+                    const bool sure = okm && !(rd < lim_sure[k]);  // dist > dthr is gated (strict); NaN is not (Q8/Q9)
+                    const bool maybe = okm && !(rd < lim_maybe[k]);
+                    const float w = (sm[i] + ss[k]) * rd;        // score / 0.0005
+                    const float t = kDistDelta * rd;             // relative half-width of the distance error
+                    const bool tight = rd <= 0.5f / kDistDelta;
+                    if (sure && tight) lo[i * kTile + k] += fmaf(-w, t, w);                      // w (1 - t)
+                    if (maybe) hi[i * kTile + k] += tight ? fmaf(w + w, t, w) : INFINITY;        // w (1 + 2t)
                 }
             }
         }
-        const float lo_tot = reduce16(lo, lane), hi_tot = reduce16(hi, lane);
+        const float lo_tot = 0.0005f * reduce16(lo, lane), hi_tot = 0.0005f * reduce16(hi, lane);
         // mean < ast  <=>  sum < ast*J.  4e-5: float32 rounding of the weights (|hm x hs|^2 from the Gram form) and
         // of the 133-term sums, relative.  Anything else (also NaN) is decided in float64 from the raw inputs.
         const double thrJ = a.prm.ast * (double)J;

@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
             const float2* kfj = kp2 + fo * R + j;
             const float* sfj = a.scores + fo * R + j;
             const uint2* mb = a.memb2 + fo * a.ncand + (start & 0x7fffffff);
-            if (__all_sync(kFull, clique)) {
+            if (clique) {  // per lane: a row's bits must not depend on which rows share its warp
                 // The pairs (x, y), x < y.  ROLLED: x in a rolled loop, y unrolled -- all 28 pairs of 8 cameras unrolled
                 // are 25 KB of straight-line code per item and 40 % of the warp stalls were instruction fetches
                 // (profiles/r2a); rolled, the body is 7 pair solves, camera x's registers are picked by a switch on

@@ -4,7 +4,7 @@ tag=${1:-r2b}; out=gpurun_out/$tag
 mkdir -p $out
 timeout 1800 python -m pytest tests -m gpu -q -x > $out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_gpu.log
 tail -12 $out/pytest_gpu.log
-for rolled in 1 0; do
+for rolled in 0; do
   SNOWTRI_MF_ROLLED=$rolled timeout 300 python bench.py --workload cfg3 --precision mixed --steps 10 --warmup 3 --no-cpu --no-e2e --no-others \
       > $out/bench_cfg3_rolled$rolled.json 2> $out/bench_cfg3_rolled$rolled.err
   python - <<PY
