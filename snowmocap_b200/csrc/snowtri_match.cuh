@@ -65,126 +65,141 @@ __device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
     return v[0] + __shfl_xor_sync(kFull, v[0], 1);
 }
 
-// One (frame, camera pair, 4 x 4 person tile) item by one warp.  `rays` / `scs` point at the frame's rays and
-// scores (shared or global memory), kf / sf at its raw inputs in global memory (float64 paths).
-__device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
-                                               const float* scs, const float2* kf, const float* sf, int f, int it, int lane) {
+// One (frame, camera pair, 4 x 4 person tile) item as a lane sees it (warp-uniform in the main loop; in the tail
+// pass every group of lanes looks at another item).
+struct MatchItem {
+    int pair, mc, sc, pm0, ps0, nm, ns;  // nm / ns: persons of the tile that are present
+    V3<float> d;                         // ts - tm
+    const float4 *rm, *rs;               // rays of the tile's first main / secondary person
+    const float *qm, *qs;                // their scores
+};
+
+__device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const double* camD, const uchar2* pairs,
+                                                   const float4* rays, const float* scs, int f, int it) {
     const int C = a.C, P = a.P, J = a.J;
     const int tpp = (P + kTile - 1) / kTile;
-    const int pair = it / (tpp * tpp), tt = it - pair * tpp * tpp;
-    const int pm0 = (tt / tpp) * kTile, ps0 = (tt % tpp) * kTile;
-    const int mc = pairs[pair].x, sc = pairs[pair].y;
-    const int cm = a.counts ? max(0, min(P, a.counts[(size_t)f * C + mc])) : P;
-    const int cs = a.counts ? max(0, min(P, a.counts[(size_t)f * C + sc])) : P;
-    const int nm = max(0, min(kTile, cm - pm0)), ns = max(0, min(kTile, cs - ps0));  // persons present in the tile
-    // lanes 2c and 2c+1 end up with candidate c = (i, k) of the tile
-    const int ci = (lane >> 3) & 3, ck = (lane >> 1) & 3;
-    const bool present = ci < nm && ck < ns;
-    bool kept = present;
+    MatchItem t;
+    t.pair = it / (tpp * tpp);
+    const int tt = it - t.pair * tpp * tpp;
+    t.pm0 = (tt / tpp) * kTile;
+    t.ps0 = (tt % tpp) * kTile;
+    t.mc = pairs[t.pair].x;
+    t.sc = pairs[t.pair].y;
+    const int cm = a.counts ? max(0, min(P, a.counts[(size_t)f * C + t.mc])) : P;
+    const int cs = a.counts ? max(0, min(P, a.counts[(size_t)f * C + t.sc])) : P;
+    t.nm = max(0, min(kTile, cm - t.pm0));
+    t.ns = max(0, min(kTile, cs - t.ps0));
+    t.d.x = (float)(camD[12 * t.sc + 9] - camD[12 * t.mc + 9]);
+    t.d.y = (float)(camD[12 * t.sc + 10] - camD[12 * t.mc + 10]);
+    t.d.z = (float)(camD[12 * t.sc + 11] - camD[12 * t.mc + 11]);
+    t.rm = rays + (size_t)(t.mc * P + t.pm0) * J;
+    t.rs = rays + (size_t)(t.sc * P + t.ps0) * J;
+    t.qm = scs + (size_t)(t.mc * P + t.pm0) * J;
+    t.qs = scs + (size_t)(t.sc * P + t.ps0) * J;
+    return t;
+}
 
-    if (!a.all_kept && nm > 0 && ns > 0) {  // ast <= 0 with kst >= 0 can never reject: no sums needed
-        // Two running sums per candidate, a LOWER and an UPPER bound of its float64 score sum.  A joint's score is
-        // c/dist and the float32 ray distance is good to kDistDelta metres, so with t = kDistDelta/dist the true score
-        // lies in [w/(1+t), w/(1-t)] which contains [w(1-t), w(1+2t)] for t <= 1/2 (beyond that the joint adds nothing
-        // to the lower bound and +inf to the upper).  A joint whose gate sits inside its guard band counts in the
-        // upper bound only.  One-sided bounds
-        // matter: scores are heavy-tailed (rays that happen to pass within 0.01 mm score 80 +- 80), which blows up
-        // a symmetric error bar -- with it every fourth correctly matched candidate went to the float64 path
-        // (profiles/r2a) -- but not the lower bound, and "kept" only needs the lower bound above the threshold.
-        float lo[kTile * kTile], hi[kTile * kTile];
+// Gate on 1/dist, pulled in / pushed out by the guard band: a joint surely passes at 1/dist >= r_sure, may pass at
+// 1/dist >= r_maybe.  The band is the float32 error of the distance (kGateGuard, relative) or the distance error bound
+// relative to a small threshold, whichever is wider.
+struct MatchGate {
+    float r_sure, r_maybe;
+    __device__ explicit MatchGate(double dthr) {
+        const float guard = fmaxf(kGateGuard, 4.f * kDistDelta / (float)dthr);
+        r_sure = (float)(1.0 / dthr) * (1.f + guard);
+        r_maybe = (float)(1.0 / dthr) * (1.f - guard);
+    }
+};
+
+// The 16 candidates of the tile at joint j of this lane: two running sums per candidate, a LOWER and an UPPER bound
+// of its float64 score sum (in units of 0.0005).  A joint's score is c/dist and the float32 ray distance is good to
+// kDistDelta metres, so with t = kDistDelta/dist the true score lies in [w/(1+t), w/(1-t)], which contains
+// [w(1-t), w(1+2t)] for t <= 1/2 (beyond that the joint adds nothing to the lower bound and +inf to the upper).  A
+// joint whose gate sits inside its guard band counts in the upper bound only.  One-sided bounds matter: scores are
+// heavy-tailed (rays that happen to pass within 0.01 mm score 80 +- 80), which blows up a symmetric error bar -- with
+// it every fourth correctly matched candidate went to the float64 path (profiles/r2a) -- but not the lower bound, and
+// "kept" only needs the lower bound above the threshold.
+// Straight-line and predicated: a vote around the score arithmetic does not pay -- with 32 joints per warp some lane
+// of a wrongly matched pair passes the 5 cm gate two times out of three (the voted branch ran for 65 % of the
+// evaluations and serialised their dependency chains, profiles/r2b).
+__device__ __forceinline__ void match_eval(const MatchItem& t, int J, int j, bool valid, const MatchGate& g,
+                                           float (&lo)[kTile * kTile], float (&hi)[kTile * kTile]) {
+    float4 m[kTile], s[kTile];
+    float sm[kTile], ss[kTile], lim_sure[kTile], lim_maybe[kTile];
 #pragma unroll
-        for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
-        V3<float> d;
-        d.x = (float)(camD[12 * sc + 9] - camD[12 * mc + 9]);
-        d.y = (float)(camD[12 * sc + 10] - camD[12 * mc + 10]);
-        d.z = (float)(camD[12 * sc + 11] - camD[12 * mc + 11]);
-        // gate on 1/dist, pulled in / pushed out by the guard band: a joint surely passes at 1/dist >= r_sure, may pass
-        // at 1/dist >= r_maybe.  The band is the float32 error of the distance (kGateGuard, relative) or the distance
-        // error bound relative to a small threshold, whichever is wider.
-        const float guard = fmaxf(kGateGuard, 4.f * kDistDelta / (float)a.prm.dthr);
-        const float r_sure = (float)(1.0 / a.prm.dthr) * (1.f + guard), r_maybe = (float)(1.0 / a.prm.dthr) * (1.f - guard);
-        const float4* rm = rays + (size_t)(mc * P + pm0) * J;
-        const float4* rs = rays + (size_t)(sc * P + ps0) * J;
-        const float* qm = scs + (size_t)(mc * P + pm0) * J;
-        const float* qs = scs + (size_t)(sc * P + ps0) * J;
-        for (int j0 = 0; j0 < J; j0 += 32) {
-            const bool valid = j0 + lane < J;
-            const int j = valid ? j0 + lane : J - 1;
-            float4 m[kTile], s[kTile];
-            float sm[kTile], ss[kTile];
+    for (int i = 0; i < kTile; ++i) {  // persons beyond the count alias person 0 of the tile and are masked
+        const int r = i < t.nm ? i : 0;
+        m[i] = t.rm[(size_t)r * J + j];
+        sm[i] = t.qm[(size_t)r * J + j];
+    }
 #pragma unroll
-            for (int i = 0; i < kTile; ++i) {  // persons beyond the count alias person 0 of the tile and are masked
-                const int r = i < nm ? i : 0;
-                m[i] = rm[(size_t)r * J + j];
-                sm[i] = qm[(size_t)r * J + j];
-            }
+    for (int k = 0; k < kTile; ++k) {
+        const int r = k < t.ns ? k : 0;
+        s[k] = t.rs[(size_t)r * J + j];
+        ss[k] = t.qs[(size_t)r * J + j];
+        // a secondary ray with a low score (it carries -|hs|^2) or beyond the count is gated through its limits
+        const bool oks = k < t.ns && !(s[k].w < 0.f);
+        lim_sure[k] = oks ? g.r_sure : INFINITY;
+        lim_maybe[k] = oks ? g.r_maybe : INFINITY;
+        s[k].w = fabsf(s[k].w);
+    }
 #pragma unroll
-            for (int k = 0; k < kTile; ++k) {
-                const int r = k < ns ? k : 0;
-                s[k] = rs[(size_t)r * J + j];
-                ss[k] = qs[(size_t)r * J + j];
-                if (k >= ns) s[k].w = -1.f;
-            }
-            // a secondary ray with a low score (it carries -|hs|^2) or beyond the count is gated through its limits
-            float lim_sure[kTile], lim_maybe[kTile];
+    for (int i = 0; i < kTile; ++i) {
+        const bool okm = valid && i < t.nm && !(m[i].w < 0.f);
+        V3<float> e;  // d x hm:  d.(hm x hs) = hs.(d x hm)
+        e.x = fmaf(t.d.y, m[i].z, -(t.d.z * m[i].y));
+        e.y = fmaf(t.d.z, m[i].x, -(t.d.x * m[i].z));
+        e.z = fmaf(t.d.x, m[i].y, -(t.d.y * m[i].x));
 #pragma unroll
-            for (int k = 0; k < kTile; ++k) {
-                const bool oks = !(s[k].w < 0.f);
-                lim_sure[k] = oks ? r_sure : INFINITY;
-                lim_maybe[k] = oks ? r_maybe : INFINITY;
-                s[k].w = fabsf(s[k].w);
-            }
-            // Straight-line, predicated: a vote around the score arithmetic does not pay -- with 32 joints per warp
-            // some lane of a wrongly matched pair passes the 5 cm gate two times out of three (measured: the voted
-            // branch ran for 65 % of the evaluations and serialised their dependency chains, profiles/r2b).
-#pragma unroll
-            for (int i = 0; i < kTile; ++i) {
-                const bool okm = valid && i < nm && !(m[i].w < 0.f);
-                V3<float> e;  // d x hm:  d.(hm x hs) = hs.(d x hm)
-                e.x = fmaf(d.y, m[i].z, -(d.z * m[i].y));
-                e.y = fmaf(d.z, m[i].x, -(d.x * m[i].z));
-                e.z = fmaf(d.x, m[i].y, -(d.y * m[i].x));
-#pragma unroll
-                for (int k = 0; k < kTile; ++k) {
-                    const float B = fmaf(m[i].x, s[k].x, fmaf(m[i].y, s[k].y, m[i].z * s[k].z));
-                    const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
-                    const float nn = fmaf(m[i].w, s[k].w, -(B * B));  // |hm x hs|^2
-                    const float rd = nn * rsqrt_fast(nn * (dn * dn));  // sqrt(n.n)/|d.n| = 1/dist
-                    const bool sure = okm && !(rd < lim_sure[k]);  // dist > dthr is gated (strict); NaN is not (Q8/Q9)
-                    const bool maybe = okm && !(rd < lim_maybe[k]);
-                    const float w = (sm[i] + ss[k]) * rd;        // score / 0.0005
-                    const float t = kDistDelta * rd;             // relative half-width of the distance error
-                    const bool tight = rd <= 0.5f / kDistDelta;
-                    if (sure && tight) lo[i * kTile + k] += fmaf(-w, t, w);                      // w (1 - t)
-                    if (maybe) hi[i * kTile + k] += tight ? fmaf(w + w, t, w) : INFINITY;        // w (1 + 2t)
-                }
-            }
+        for (int k = 0; k < kTile; ++k) {
+            const float B = fmaf(m[i].x, s[k].x, fmaf(m[i].y, s[k].y, m[i].z * s[k].z));
+            const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
+            const float nn = fmaf(m[i].w, s[k].w, -(B * B));   // |hm x hs|^2
+            const float rd = nn * rsqrt_fast(nn * (dn * dn));  // sqrt(n.n)/|d.n| = 1/dist
+            const bool sure = okm && !(rd < lim_sure[k]);      // dist > dthr is gated (strict); NaN is not (Q8/Q9)
+            const bool maybe = okm && !(rd < lim_maybe[k]);
+            const float w = (sm[i] + ss[k]) * rd;              // score / 0.0005
+            const float tt = kDistDelta * rd;                  // relative half-width of the distance error
+            const bool tight = rd <= 0.5f / kDistDelta;
+            if (sure && tight) lo[i * kTile + k] += fmaf(-w, tt, w);                  // w (1 - t)
+            if (maybe) hi[i * kTile + k] += tight ? fmaf(w + w, tt, w) : INFINITY;    // w (1 + 2t)
         }
-        const float lo_tot = 0.0005f * reduce16(lo, lane), hi_tot = 0.0005f * reduce16(hi, lane);
+    }
+}
+
+// Decision of the tile's 16 candidates from the reduced bounds (lanes 2c and 2c+1 hold candidate c = (i, k) of the
+// tile), float64 re-evaluation where the bounds straddle the threshold, keep byte of every candidate slot of the tile
+// and float64 centre-joint midpoint of the kept ones (reference :112,124).  `t` is warp-uniform here.
+__device__ __forceinline__ void match_decide(const GenArgs& a, const double* camD, const float2* kf, const float* sf, int f,
+                                             const MatchItem& t, bool have_sums, float lo_tot, float hi_tot, int lane) {
+    const int P = a.P, J = a.J;
+    const int ci = (lane >> 3) & 3, ck = (lane >> 1) & 3;
+    const bool present = ci < t.nm && ck < t.ns;
+    bool kept = present;  // ast <= 0 with kst >= 0 can never reject (all_kept): no sums were needed
+    if (have_sums) {
         // mean < ast  <=>  sum < ast*J.  4e-5: float32 rounding of the weights (|hm x hs|^2 from the Gram form) and
         // of the 133-term sums, relative.  Anything else (also NaN) is decided in float64 from the raw inputs.
         const double thrJ = a.prm.ast * (double)J;
-        const bool surely_kept = (double)lo_tot * (1.0 - 4e-5) >= thrJ, surely_not = (double)hi_tot * (1.0 + 4e-5) < thrJ;
+        const bool surely_kept = (double)(0.0005f * lo_tot) * (1.0 - 4e-5) >= thrJ;
+        const bool surely_not = (double)(0.0005f * hi_tot) * (1.0 + 4e-5) < thrJ;
         kept = present && surely_kept;
         unsigned redo = __ballot_sync(kFull, present && !(lane & 1) && !surely_kept && !surely_not);
         while (redo) {  // discrete decision: the whole warp redoes this candidate in float64
             const int l = __ffs(redo) - 1;
             redo &= redo - 1;
             const int cc = l >> 1;
-            const double mean = gen_candidate_mean_f64(a, camD, kf, sf, mc, pm0 + (cc >> 2), sc, ps0 + (cc & 3), lane);
+            const double mean = gen_candidate_mean_f64(a, camD, kf, sf, t.mc, t.pm0 + (cc >> 2), t.sc, t.ps0 + (cc & 3), lane);
             if ((lane >> 1) == cc) kept = !(mean < a.prm.ast);  // NaN mean is kept (Q9)
         }
     }
-
-    // keep byte of every candidate slot of the tile, float64 centre-joint midpoint of the kept ones (reference :112,124)
-    const int pm = pm0 + ci, ps = ps0 + ck;
+    const int pm = t.pm0 + ci, ps = t.ps0 + ck;
     if (!(lane & 1) && pm < P && ps < P) {
-        const size_t n = (size_t)f * a.ncand + ((size_t)pair * P + pm) * P + ps;
+        const size_t n = (size_t)f * a.ncand + ((size_t)t.pair * P + pm) * P + ps;
         a.keep[n] = kept ? 1 : 0;
         if (kept) {
-            const float2 q0 = kf[(size_t)(mc * P + pm) * J + a.prm.center], q1 = kf[(size_t)(sc * P + ps) * J + a.prm.center];
-            const double* c0 = camD + 12 * mc;
-            const double* c1 = camD + 12 * sc;
+            const float2 q0 = kf[(size_t)(t.mc * P + pm) * J + a.prm.center], q1 = kf[(size_t)(t.sc * P + ps) * J + a.prm.center];
+            const double* c0 = camD + 12 * t.mc;
+            const double* c1 = camD + 12 * t.sc;
             const V3<double> h0 = back_project<double>(c0, (double)q0.x, (double)q0.y);
             const V3<double> h1 = back_project<double>(c1, (double)q1.x, (double)q1.y);
             V3<double> dd, mid;
@@ -196,6 +211,90 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
             c3[0] = w.x;
             c3[1] = w.y;
             c3[2] = w.z;
+        }
+    }
+}
+
+// One item by one warp, joints in chunks of 32 (the last one partly idle).
+__device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
+                                               const float* scs, const float2* kf, const float* sf, int f, int it, int lane) {
+    const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
+    const bool sums = !a.all_kept && t.nm > 0 && t.ns > 0;
+    float lo_tot = 0.f, hi_tot = 0.f;
+    if (sums) {
+        const MatchGate g(a.prm.dthr);
+        float lo[kTile * kTile], hi[kTile * kTile];
+#pragma unroll
+        for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
+        for (int j0 = 0; j0 < a.J; j0 += 32) {
+            const bool valid = j0 + lane < a.J;
+            match_eval(t, a.J, valid ? j0 + lane : a.J - 1, valid, g, lo, hi);
+        }
+        lo_tot = reduce16(lo, lane);
+        hi_tot = reduce16(hi, lane);
+    }
+    match_decide(a, camD, kf, sf, f, t, sums, lo_tot, hi_tot, lane);
+}
+
+constexpr int kTailGroup = 4;  // items whose last, partly filled chunk of joints share one pass (shared-memory kernel)
+
+// Up to kTailGroup items of one warp (it0, it0 + stride, ...): their full 32-joint chunks one item at a time, then
+// the J % 32 joints that are left of ALL of them in one pass -- lane = (item of the group, joint) -- instead of one
+// mostly idle chunk per item (133 joints: 5 of 32 lanes busy).  The tail sums travel through `scratch`
+// (32 x 17 floats of this warp) to the lanes that hold the candidates.
+__device__ __forceinline__ void gen_match_group(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
+                                                const float* scs, const float2* kf, const float* sf, int f, int it0,
+                                                int stride, int items, int tg, float* scratch, int lane) {
+    const int J = a.J, tail = J & 31, jfull = J - tail;
+    const MatchGate g(a.prm.dthr);
+    float lo_tot[kTailGroup], hi_tot[kTailGroup];
+#pragma unroll
+    for (int q = 0; q < kTailGroup; ++q) {
+        lo_tot[q] = hi_tot[q] = 0.f;
+        const int it = it0 + q * stride;
+        if (q < tg && it < items) {
+            const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
+            if (!a.all_kept && t.nm > 0 && t.ns > 0) {
+                float lo[kTile * kTile], hi[kTile * kTile];
+#pragma unroll
+                for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
+                for (int j0 = 0; j0 < jfull; j0 += 32) match_eval(t, J, j0 + lane, true, g, lo, hi);
+                lo_tot[q] = reduce16(lo, lane);
+                hi_tot[q] = reduce16(hi, lane);
+            }
+        }
+    }
+    if (!a.all_kept) {  // the tails: lane -> (item q of the group, joint jfull + jt)
+        const int q = lane / tail, jt = lane - q * tail;
+        const int it = it0 + q * stride;
+        const bool live = q < tg && it < items;
+        const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, live ? it : it0);
+        float lo[kTile * kTile], hi[kTile * kTile];
+#pragma unroll
+        for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
+        match_eval(t, J, jfull + jt, live && t.nm > 0 && t.ns > 0, g, lo, hi);
+        const int c = (lane >> 1) & 15;
+#pragma unroll
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+            for (int i = 0; i < kTile * kTile; ++i) scratch[lane * 17 + i] = pass ? hi[i] : lo[i];
+            __syncwarp();
+#pragma unroll
+            for (int qq = 0; qq < kTailGroup; ++qq) {
+                float sum = 0.f;
+                for (int u = 0; u < tail; ++u) sum += qq < tg ? scratch[(qq * tail + u) * 17 + c] : 0.f;
+                if (pass) hi_tot[qq] += sum;
+                else lo_tot[qq] += sum;
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kTailGroup; ++q) {
+        const int it = it0 + q * stride;
+        if (q < tg && it < items) {
+            const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
+            match_decide(a, camD, kf, sf, f, t, !a.all_kept && t.nm > 0 && t.ns > 0, lo_tot[q], hi_tot[q], lane);
         }
     }
 }
@@ -250,7 +349,15 @@ __global__ void __launch_bounds__(224, 2) gen_match_smem_kernel(const __grid_con
     __syncthreads();
     const int tpp = (P + kTile - 1) / kTile;
     const int items = a.npairs * tpp * tpp;
-    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it, lane);
+    const int tail = J & 31;
+    const int tg = tail > 0 && tail <= 16 ? min(kTailGroup, 32 / tail) : 0;  // items per tail pass
+    if (tg >= 2) {
+        float* scratch = reinterpret_cast<float*>(scs + R) + warp * (32 * 17);
+        for (int it0 = warp; it0 < items; it0 += NW * tg)
+            gen_match_group(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it0, NW, items, tg, scratch, lane);
+    } else {
+        for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it, lane);
+    }
 }
 
 // Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident

@@ -888,7 +888,7 @@ def test_random_configurations_vs_c_oracle(torch_cuda, seed):
 # ---- final all-gather through the C ABI -----------------------------------------------------------
 def test_native_allgather_single_rank(torch_cuda):
     """snowtri_comm_unique_id / snowtri_comm_init / snowtri_allgather with a one-rank communicator (the round-end GPU
-    box has one GPU; tools/allgather_check.py is the 2-rank check)."""
+    box has one GPU; tools/mgpu_check.py under tests/test_multi_gpu.py is the multi-rank check)."""
     torch = torch_cuda
     import ctypes as ct
     from snowmocap_b200 import _lib

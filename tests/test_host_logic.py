@@ -155,6 +155,26 @@ def test_shard_range_partitions_frames():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_shard_cyclic_pieces_tile_the_clip_in_gather_order():
+    """Piece k of every rank, concatenated in rank order, is the k-th contiguous stretch of the clip: an all-gather of
+    piece k lands in place."""
+    for world in (1, 2, 4, 8):
+        for nch in (1, 3, 5):
+            F = world * nch * 7
+            spans = [sdist.shard_cyclic(F, r, world, nch) for r in range(world)]
+            c = F // (world * nch)
+            seen = []
+            for k in range(nch):
+                for r in range(world):
+                    lo, hi = spans[r][k]
+                    assert hi - lo == c
+                    seen.append((lo, hi))
+            assert seen[0][0] == 0 and seen[-1][1] == F
+            assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))
+    with pytest.raises(ValueError):
+        sdist.shard_cyclic(10, 0, 4, 3)
+
+
 # ---- world_size-2 gloo: sharding + all-gather reproduces the single-process result -------------
 def _free_port():
     s = socket.socket()

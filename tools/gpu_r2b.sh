@@ -38,3 +38,18 @@ for kre in gen_match_smem_kernel mfuse_kernel; do
     python bench.py --workload cfg3 --precision mixed --steps 2 --warmup 3 --no-cpu --no-e2e --no-others > $out/ncu_$kre.log 2>&1
   tail -1 $out/ncu_$kre.log | cut -c1-200
 done
+# 4. the full default bench line (new bench.py), N = 1
+timeout 900 python bench.py > $out/bench_default.json 2> $out/bench_default.err; echo "bench rc=$?"
+python - <<PY
+import json
+try:
+    d=json.load(open("$out/bench_default.json"))
+    print("cfg2", "value=%.3e"%d["value"], "frac=%.3f"%d["roofline"]["frac"], "e2e=%.3e"%d["e2e"]["value"], "ceil frac", d["e2e"].get("frac_of_copy_ceiling"), d["e2e"].get("dropin"))
+    print(" parity", d["parity"])
+    print(" cpu", json.dumps(d.get("cpu_baseline"))[:600])
+    s=d["secondary"]
+    for k,v in s.items():
+        print(k, json.dumps(v)[:1500])
+except Exception as e:
+    print("default bench failed", e); print(open("$out/bench_default.err").read()[-3000:])
+PY

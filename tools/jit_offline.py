@@ -31,8 +31,13 @@ for x in range(C - 1):
         e += 1
 inv_dthr = 1.0 / 0.05
 defs = {"P1_NI": "2"}
+TD = "float"
 for arg in sys.argv[1:]:
     k, _, v = arg.partition("=")
+    if k == "TD":          # TD=double: the mixed mode (float64 distance numerator)
+        TD = v
+        defs["P1_NI"] = "1"
+        continue
     defs[k] = v or "1"
 src = "#define P1_JIT 1\n" + "".join(f"#define {k} {v}\n" for k, v in defs.items())
 src += f"#define P1_JIT_J {J}\n#define P1_JIT_JOUT {J}\n#define P1_JIT_POUT {Pout}\n#define P1_JIT_GW {Gw}\n"
@@ -41,7 +46,7 @@ src += f"#define P1_JIT_KSCALE_FULL {0.0005 / NP:.9e}f\n"
 src += "#define P1_JIT_CAMC {" + ",".join(f"{v:.9e}f" for v in camc) + "}\n"
 src += "#define P1_JIT_PDC {" + ",".join(f"{v:.9e}f" for v in pdc) + "}\n"
 src += ('#include "snowtri_p1.cuh"\nextern "C" __global__ void __launch_bounds__(256, 2) p1_jit('
-        "const __grid_constant__ snowtri::P1Args<float, 4> a) { snowtri::p1_body<float, float, 4, 256>(a); }\n")
+        f"const __grid_constant__ snowtri::P1Args<float, 4> a) {{ snowtri::p1_body<float, {TD}, 4, 256>(a); }}\n")
 out = "/tmp/p1_jit_offline"
 open(out + ".cu", "w").write(src)
 cmd = ["nvcc", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
@@ -61,3 +66,15 @@ print("  ".join(f"{k} {v}" for k, v in ops.most_common(24)))
 # window of 1000 instructions by FFMA count as a stable proxy
 ff = [1 if i.startswith(("FFMA", "FMUL", "FADD")) else 0 for i in ins]
 print("float arithmetic instructions:", sum(ff), " MUFU:", ops.get("MUFU", 0), " LDG:", ops.get("LDG", 0), " STG:", ops.get("STG", 0))
+
+# loops: every backward branch, with its instruction count and opcode mix (the fuse loop is the big FFMA-dense one)
+addr_ops = [(int(m.group(1), 16), m.group(2).split(".")[0], m.group(0)) for m in
+            re.finditer(r"/\*([0-9a-f]{4})\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)[^;]*;", sass)]
+for a, op, text in addr_ops:
+    if op == "BRA":
+        t = re.search(r"0x([0-9a-f]+)", text.split("BRA")[1])
+        if t and int(t.group(1), 16) < a:
+            sub = [o for aa, o, _ in addr_ops if int(t.group(1), 16) <= aa <= a]
+            if len(sub) > 150:
+                print(f"loop {int(t.group(1), 16):#x}..{a:#x}: {len(sub)} instructions per step ({defs['P1_NI']} item(s) per lane):",
+                      "  ".join(f"{k} {v}" for k, v in collections.Counter(sub).most_common(16)))
