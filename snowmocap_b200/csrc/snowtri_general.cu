@@ -66,7 +66,7 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
                     long double v = 0;
                     for (int r = 0; r < 3; ++r)
                         for (int q = 0; q < 3; ++q) v += (long double)cam[12 * x + 3 * r + i] * dx[3 * r + q] * (long double)cam[12 * y + 3 * q + j2];
-                    a.E[9 * e + 3 * i + j2] = (double)(-v);
+                    a.E[10 * e + 3 * i + j2] = (double)(-v);
                 }
         }
     // pair loop fully unrolled (default) or with the first camera of a pair in a rolled loop (SNOWTRI_MF_ROLLED=1)
@@ -127,7 +127,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     const bool fuse2 = gen2 && C >= 2 && C <= 8 && Pout <= 32 && P <= 255;
     const size_t R = (size_t)C * P * J;
     const size_t mtab = MatchTables::bytes(C, a.npairs);
-    const size_t mstaged = mtab + R * 20 + 7 * 32 * 17 * 4;  // rays (16 B) + scores (4 B) of one frame, tail scratch of 7 warps
+    const size_t mstaged = mtab + R * 20 + 7 * kMatchScratch * 4;  // rays (16 B) + scores (4 B) of one frame, scratch of 7 warps
     const bool match_smem = match2 && !h->no_fly && mstaged <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024;  // two CTAs per SM
     const bool match_glob = match2 && !match_smem;
 

@@ -38,7 +38,7 @@ struct MFArgs {
     double inv_dthr64;
     alignas(16) float camc[C * 12];   // M = R*inv(K), rows padded to 4
     alignas(16) float pdc[NP * 8];    // per pair: d = ts - tm (3), pad, mid = (tm + ts)/2 (3), pad
-    alignas(16) double E[NP * 9];     // per pair: d.(hm x hs) = [um vm 1] E [us vs 1]^T
+    alignas(16) double E[NP * 10];    // per pair (stride 10: 16-byte aligned rows for 128-bit constant loads): d.(hm x hs) = [um vm 1] E [us vs 1]^T
     alignas(16) double cam64[C * 12]; // float64 M (rows padded to 4) for the rolled path; t in cam64t
     alignas(16) double cam64t[C * 4];
 };
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NT, MINB) mfuse_kernel(const __grid_constant__
                     d.x = a.pdc[e * 8]; d.y = a.pdc[e * 8 + 1]; d.z = a.pdc[e * 8 + 2];
                     const PairSolN<float> s = pair_solve_n(hx, Ax, h[y], A[y], d);
                     // d.(hm x hs) in float64 from the pixel coordinates: l = E [uy vy 1]^T, dn = [ux vx 1] l
-                    const double* E = a.E + 9 * e;
+                    const double* E = a.E + 10 * e;
                     const double l0 = fma(E[0], ud[y], fma(E[1], vd[y], E[2]));
                     const double l1 = fma(E[3], ud[y], fma(E[4], vd[y], E[5]));
                     const double l2 = fma(E[6], ud[y], fma(E[7], vd[y], E[8]));
