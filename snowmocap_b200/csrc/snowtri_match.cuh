@@ -215,7 +215,10 @@ __device__ __forceinline__ void match_decide(const GenArgs& a, const double* cam
     }
 }
 
-// One item by one warp, joints in chunks of 32 (the last one partly idle).
+// One item by one warp, joints in chunks of 32 (the last one partly idle: 5 of 32 lanes at 133 joints).  Tried and
+// dropped: the leftover joints of four items sharing one pass -- 11 % fewer instructions, but either the unrolled form
+// outgrows the instruction cache (1.33 -> 1.47 ms at BASELINE configs[2]) or the rolled form pays the saving back in
+// index arithmetic and needs more than the 128 registers two 7-warp CTAs per SM leave (2.03 ms); profiles/r2d, r2e.
 __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
                                                const float* scs, const float2* kf, const float* sf, int f, int it, int lane) {
     const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
@@ -234,73 +237,6 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
         hi_tot = reduce16(hi, lane);
     }
     match_decide(a, camD, kf, sf, f, t, sums, lo_tot, hi_tot, lane);
-}
-
-constexpr int kTailGroup = 4;                                   // items whose leftover joints share one pass
-constexpr int kMatchScratch = 32 * 17 + kTailGroup * 2 * 32;    // floats of per-warp scratch of gen_match_group
-
-// Up to kTailGroup items of one warp (it0, it0 + stride, ...): their full 32-joint chunks one item at a time, then
-// the J % 32 joints that are left of ALL of them in one pass -- lane = (item of the group, joint) -- instead of one
-// mostly idle chunk per item (133 joints: 5 of 32 lanes busy).  ONE rolled loop over the passes, so that the 540
-// instructions of match_eval exist once (unrolled over the items the kernel outgrew the instruction cache: 23 % of
-// the stalls were instruction fetches, profiles/r2d).  The reduced bounds wait in `scratch` (totals: [item][lo|hi][lane];
-// transposition area of the tail pass: 32 x 17 floats) until every item of the group has its tail.
-__device__ __forceinline__ void gen_match_group(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
-                                                const float* scs, const float2* kf, const float* sf, int f, int it0,
-                                                int stride, int items, int tg, float* scratch, int lane) {
-    const int J = a.J, tail = J & 31, jfull = J - tail, nfull = jfull >> 5;  // tg * tail <= 32
-    const MatchGate g(a.prm.dthr);
-    float* tot = scratch + 32 * 17;
-    for (int q = 0; q < tg; ++q) tot[(q * 2) * 32 + lane] = tot[(q * 2 + 1) * 32 + lane] = 0.f;
-    __syncwarp();
-    if (!a.all_kept) {
-        float lo[kTile * kTile], hi[kTile * kTile];
-        MatchItem t;
-        const int npass = tg * nfull + (tail ? 1 : 0);
-        const int tq = tail ? lane / tail : 0, tj = lane - tq * tail;  // the tail pass: lane -> (item tq, joint jfull + tj)
-#pragma unroll 1
-        for (int p = 0; p < npass; ++p) {
-            const bool is_tail = p == tg * nfull;
-            const int q = is_tail ? tq : p / nfull, chunk = is_tail ? 0 : p - q * nfull;
-            const int it = it0 + q * stride;
-            const bool live = q < tg && it < items;
-            if (chunk == 0) {
-#pragma unroll
-                for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
-                t = match_item_of(a, camD, pairs, rays, scs, f, live ? it : it0);
-            }
-            match_eval(t, J, is_tail ? jfull + tj : chunk * 32 + lane, live && t.nm > 0 && t.ns > 0, g, lo, hi);
-            if (is_tail) {  // per-lane sums of different items: through the transposition area to the candidates' lanes
-                const int c = (lane >> 1) & 15;
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-#pragma unroll
-                    for (int i = 0; i < kTile * kTile; ++i) scratch[lane * 17 + i] = pass ? hi[i] : lo[i];
-                    __syncwarp();
-                    for (int qq = 0; qq < tg; ++qq) {
-                        float sum = 0.f;
-                        for (int u = 0; u < tail; ++u) sum += scratch[(qq * tail + u) * 17 + c];
-                        tot[(qq * 2 + pass) * 32 + lane] += sum;
-                    }
-                    __syncwarp();
-                }
-            } else if (chunk == nfull - 1) {  // warp-uniform
-                const float l = reduce16(lo, lane), h = reduce16(hi, lane);
-                tot[(q * 2) * 32 + lane] = l;
-                tot[(q * 2 + 1) * 32 + lane] = h;
-            }
-        }
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int q = 0; q < tg; ++q) {
-        const int it = it0 + q * stride;
-        if (it < items) {
-            const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
-            match_decide(a, camD, kf, sf, f, t, !a.all_kept && t.nm > 0 && t.ns > 0, tot[(q * 2) * 32 + lane],
-                         tot[(q * 2 + 1) * 32 + lane], lane);
-        }
-    }
 }
 
 // Shared-memory tables of the match kernels: camera matrices and centres in float64 (C*12), the pair table.
@@ -325,7 +261,7 @@ struct MatchTables {
 // Frames whose rays fit in shared memory (20 bytes per ray): one CTA per frame builds them once and its warps walk the
 // (camera pair, tile) items out of shared memory.  Two CTAs per SM: one CTA's ray build (global loads) and decisions
 // overlap the other's arithmetic.
-__global__ void __maxnreg__(144) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
+__global__ void __launch_bounds__(224, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     MatchTables tb(smem, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
@@ -353,11 +289,7 @@ __global__ void __maxnreg__(144) gen_match_smem_kernel(const __grid_constant__ G
     __syncthreads();
     const int tpp = (P + kTile - 1) / kTile;
     const int items = a.npairs * tpp * tpp;
-    const int tail = J & 31;
-    const int tg = tail ? min(kTailGroup, 32 / tail) : kTailGroup;  // items per group (their leftover joints fit one pass)
-    float* scratch = reinterpret_cast<float*>(scs + R) + warp * kMatchScratch;
-    for (int it0 = warp; it0 < items; it0 += NW * tg)
-        gen_match_group(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it0, NW, items, tg, scratch, lane);
+    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it, lane);
 }
 
 // Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident

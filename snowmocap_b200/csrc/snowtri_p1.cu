@@ -62,6 +62,18 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
                 a.pdc[e * 8 + k] = (T)(ts - tm);
                 a.pdc[e * 8 + 4 + k] = (T)((tm + ts) / 2);
             }
+            // d.(hm x hs) = -hm^T [d]x hs  with hm = Mx [u v 1]^T, hs = My [u v 1]^T   =>   E = -Mx^T [d]x My
+            const double* cam = h->cam_host;
+            long double d[3];
+            for (int k = 0; k < 3; ++k) d[k] = (long double)cam[12 * y + 9 + k] - (long double)cam[12 * x + 9 + k];
+            const long double dx[9] = {0, -d[2], d[1], d[2], 0, -d[0], -d[1], d[0], 0};
+            for (int i = 0; i < 3; ++i)
+                for (int j2 = 0; j2 < 3; ++j2) {
+                    long double v = 0;
+                    for (int r = 0; r < 3; ++r)
+                        for (int q = 0; q < 3; ++q) v += (long double)cam[12 * x + 3 * r + i] * dx[3 * r + q] * (long double)cam[12 * y + 3 * q + j2];
+                    a.E64[10 * e + 3 * i + j2] = (double)(-v);
+                }
         }
     auto kern = p1_kernel<T, TD, C, NT>;
     int occ = 0;

@@ -81,6 +81,10 @@ struct P1Args {
     alignas(16) T pdc[NP * 8];         // per pair: d = ts - tm (3), pad, mid = (tm + ts)/2 (3), pad
     alignas(16) double cam64[C * 12];  // float64 copies: clustering centres, guard band, mixed mode
     alignas(16) double pd64[NP * 8];
+    // mixed mode: d.(hm x hs) = [um vm 1] E [us vs 1]^T with E = -Mm^T [d]x Ms per pair (rows of 3, stride 10), composed
+    // on the host in extended precision: the float64 distance numerator straight from the pixel coordinates (8 DFMA
+    // per pair, no float64 rays)
+    alignas(16) double E64[NP * 10];
     unsigned char px[NP], py[NP];
 };
 
@@ -343,7 +347,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
         int gacc = g[0];
         for (int q0 = 0; q0 < nitems; q0 += 32 * NI) {
             V3<T> h[NI][C];
-            V3<TD> hd[NI][MIXED ? C : 1];
+            TD ud[NI][MIXED ? C : 1], vd[NI][MIXED ? C : 1];  // mixed: pixel coordinates in float64
             T A[NI][C], sc[NI][C];
             int off[NI];
             bool live[NI];
@@ -356,8 +360,10 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                     h[u][c].x = fma(P1_CAMC(T, 12 * c + 0), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 1), (T)p2n[u][c].y, m2[c][0]));
                     h[u][c].y = fma(P1_CAMC(T, 12 * c + 4), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 5), (T)p2n[u][c].y, m2[c][1]));
                     h[u][c].z = fma(P1_CAMC(T, 12 * c + 8), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 9), (T)p2n[u][c].y, m2[c][2]));
-                    if constexpr (MIXED)
-                        hd[u][c] = back_project4<TD>(a.cam64 + 12 * c, (TD)p2n[u][c].x, (TD)p2n[u][c].y);
+                    if constexpr (MIXED) {
+                        ud[u][c] = (TD)p2n[u][c].x;
+                        vd[u][c] = (TD)p2n[u][c].y;
+                    }
                     A[u][c] = dot3(h[u][c], h[u][c]);
                     // a score below the keypoint threshold kills every pair of its camera: poison it so that
                     // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
@@ -431,10 +437,12 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                 d.x = P1_PDC(T, e * 8); d.y = P1_PDC(T, e * 8 + 1); d.z = P1_PDC(T, e * 8 + 2);
                 const PairSolN<T> s = pair_solve_n(h[u][x], A[u][x], h[u][y], A[u][y], d);
                 T dn;
-                if constexpr (MIXED) {
-                    V3<TD> dd;
-                    dd.x = a.pd64[e * 8]; dd.y = a.pd64[e * 8 + 1]; dd.z = a.pd64[e * 8 + 2];
-                    dn = (T)cross_dot(hd[u][x], hd[u][y], dd);
+                if constexpr (MIXED) {  // l = E [uy vy 1]^T, d.n = [ux vx 1] l
+                    const double* E = a.E64 + 10 * e;
+                    const TD l0 = fma(E[0], ud[u][y], fma(E[1], vd[u][y], E[2]));
+                    const TD l1 = fma(E[3], ud[u][y], fma(E[4], vd[u][y], E[5]));
+                    const TD l2 = fma(E[6], ud[u][y], fma(E[7], vd[u][y], E[8]));
+                    dn = (T)fma(l0, ud[u][x], fma(l1, vd[u][x], l2));
                 } else {
                     dn = cross_dot(h[u][x], h[u][y], d);
                 }
