@@ -115,27 +115,42 @@ def all_gather_frames_native(engine, local, world, stream=None):
 def triangulate_cyclic_overlapped(engine, pieces, local, full, world, comm_stream, Pout=None, keypoint_num=None):
     """Block-cyclic sharded run with the final all-gather of the 3D joints overlapped with the compute (north_star:
     "NCCL over NVLink appears only as a final all-gather of 3D joints"): piece k of this rank (``shard_cyclic``) is
-    triangulated on the current stream, then its ``out`` / ``pscores`` / ``nout`` blocks are all-gathered with
-    ``snowtri_allgather`` on ``comm_stream`` while piece k+1 is being computed.
+    triangulated on the current stream, then its ``out`` block is all-gathered with ``snowtri_allgather`` on
+    ``comm_stream`` while piece k+1 is being computed; the small ``pscores`` / ``nout`` arrays of all pieces travel in
+    one gather each after the last piece.
 
       pieces  [(kpts_k, scores_k, counts_k or None), ...] device tensors of this rank, c frames each
-      local   [dict(out, pscores, nout), ...] per-piece result buffers of this rank
+      local   dict(out (n*c,Pout,Jout,4), pscores (n*c,Pout), nout (n*c,)) -- this rank's results, piece k at rows
+              [k*c, (k+1)*c); or a list of n such dicts, one per piece (then everything is gathered piece by piece)
       full    dict(out (F,Pout,Jout,4), pscores (F,Pout), nout (F,)) -- the gathered clip, frames in global order
 
     ``init_native_comm(engine)`` first.  The current stream waits for the last gather before returning."""
     from . import _lib
     main = torch.cuda.current_stream(engine.device)
+    n = len(pieces)
     c = pieces[0][1].shape[0] if pieces else 0
-    for k, (kp, sc, cn) in enumerate(pieces):
-        engine.run(kp, sc, cn, Pout=Pout, keypoint_num=keypoint_num, out=local[k])
-        ev = torch.cuda.Event()
-        ev.record(main)
-        comm_stream.wait_event(ev)
-        lo = k * world * c
-        with torch.cuda.device(engine.device):
-            for name in ("out", "pscores", "nout"):
-                src, dst = local[k][name], full[name][lo:lo + world * c]
-                _lib.check(engine._lib.snowtri_allgather(engine._h, src.data_ptr(), dst.data_ptr(),
-                                                         src.numel() * src.element_size(), None, comm_stream.cuda_stream),
-                           engine._h)
+    per_piece = isinstance(local, (list, tuple))
+
+    def gather(src, dst):
+        _lib.check(engine._lib.snowtri_allgather(engine._h, src.data_ptr(), dst.data_ptr(), src.numel() * src.element_size(),
+                                                 None, comm_stream.cuda_stream), engine._h)
+
+    with torch.cuda.device(engine.device):
+        for k, (kp, sc, cn) in enumerate(pieces):
+            loc = local[k] if per_piece else {name: t[k * c:(k + 1) * c] for name, t in local.items()}
+            engine.run(kp, sc, cn, Pout=Pout, keypoint_num=keypoint_num, out=loc)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            comm_stream.wait_event(ev)
+            lo = k * world * c
+            for name in (("out", "pscores", "nout") if per_piece else ("out",)):
+                gather(loc[name], full[name][lo:lo + world * c])
+        if not per_piece and n:
+            # rank-major (world, n, c, ...) from one gather of every small array; the clip wants piece-major (n, world, c, ...)
+            with torch.cuda.stream(comm_stream):
+                for name in ("pscores", "nout"):
+                    tmp = torch.empty((world,) + tuple(local[name].shape), dtype=local[name].dtype, device=engine.device)
+                    gather(local[name], tmp)
+                    shape = tuple(local[name].shape[1:])
+                    full[name].view((n, world, c) + shape).copy_(tmp.view((world, n, c) + shape).transpose(0, 1))
     main.wait_stream(comm_stream)

@@ -65,6 +65,13 @@ def case(name, rig, P, J, pout, prm, precision, Ft, pieces_n, exact_pscores):
     else:  # the single-person kernel's person score is a float32 sum whose lane partition depends on the tile
         ok2 = ok2 and bool(torch.allclose(full["pscores"], one["pscores"], rtol=1e-5, atol=1e-7))
     res["cyclic_overlapped_equal"] = ok2
+    # the same with one local result array (small arrays gathered once after the last piece)
+    loc_all, full2 = new_out(c * len(spans), pout, J), new_out(Ft, pout, J)
+    triangulate_cyclic_overlapped(eng, pieces, loc_all, full2, world, comm, Pout=pout)
+    torch.cuda.synchronize()
+    ok3 = all(bool(torch.equal(full2[k], full[k])) for k in ("out", "pscores", "nout"))
+    res["cyclic_single_buffer_equal"] = ok3
+    ok2 = ok2 and ok3
     res["mean_persons"] = float(one["nout"].float().mean().item())
     eng.close()
     return res, ok and ok2
