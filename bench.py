@@ -498,10 +498,12 @@ def traffic_of(key):
             entry = json.load(fh).get(key)
         if not isinstance(entry, dict):
             return None, "no capture with provenance for this kernel"
-        with open(os.path.join(ROOT, entry["source"]), "rb") as fh:
-            sha = hashlib.sha256(fh.read()).hexdigest()[:16]
-        if sha != entry["source_sha16"]:
-            return None, f"stale: {entry['source']} changed since the capture at {entry['commit']}"
+        h = hashlib.sha256()
+        for src in entry["source"]:
+            with open(os.path.join(ROOT, src), "rb") as fh:
+                h.update(fh.read())
+        if h.hexdigest()[:16] != entry["source_sha16"]:
+            return None, f"stale: {', '.join(entry['source'])} changed since the capture at {entry['commit']}"
         return entry["bytes"], f"ncu --set full at commit {entry['commit']} ({entry['profile']})"
     except Exception as e:
         return None, f"unavailable: {e}"

@@ -14,6 +14,9 @@ import json
 import numpy as np
 
 
+_warned_cast = [False]
+
+
 class Camera:
     """Parameter container: K (3,3), R (3,3) camera->world, t (3,1) camera centre, D (1,5)."""
 
@@ -84,7 +87,19 @@ class CameraGroup:
 
     # -- per-frame observation store (reference camera.py:234-261) -----------------------------
     def add_human_2D_points(self, person, scores, camera_index, ax=None):
-        """Record one detected person (J,2) with per-keypoint scores (J,) for ``camera_index``."""
+        """Record one detected person (J,2) with per-keypoint scores (J,) for ``camera_index``.
+
+        Input contract: keypoints and scores are stored as float32 (what pose detectors emit; the engine's input
+        layout).  The reference keeps whatever dtype it is handed and back-projects in float64, so float64 keypoints
+        lose ~1e-7 relative pixel precision here and a score within one float32 ulp of ``keypoint_score_threshold``
+        can fall on the other side of it.  A lossy cast warns once."""
+        person = np.asarray(person)
+        if person.dtype == np.float64 and not _warned_cast[0] and person.size and \
+                not np.array_equal(person.astype(np.float32).astype(np.float64), person):
+            import warnings
+            warnings.warn("snowmocap_b200: float64 keypoints are rounded to float32 (the engine's input precision); "
+                          "see CameraGroup.add_human_2D_points", stacklevel=2)
+            _warned_cast[0] = True
         cam = self.cameras[camera_index]
         cam.hrnet_points.append(np.asarray(person, dtype=np.float32).reshape(-1, 2))
         cam.hrnet_point_score.append(np.asarray(scores, dtype=np.float32).reshape(-1))

@@ -262,7 +262,11 @@ class TriangulationEngine:
 
 class SmoothState:
     """Device-resident followers of ``Human_Triangulation_Smooth`` (reference triangulation.py:4-22, 164-186)
-    for one clip: create once, then ``run`` batches of consecutive frames in order."""
+    for one clip: create once, then ``run`` batches of consecutive frames in order.
+
+    ``max_persons`` must cover the person count of the clip's FIRST frame (``max_persons >= Pout`` is always enough):
+    the reference keeps one follower per first-frame person; a first frame with more persons than ``max_persons`` gets
+    followers for the first ``max_persons`` only and the others stay unsmoothed on later frames, silently."""
 
     def __init__(self, engine, max_persons, J, f=2.0, z=0.75, r=0.0):
         self._eng, self._lib, self._s = engine, engine._lib, ct.c_void_p()

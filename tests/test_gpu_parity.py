@@ -249,7 +249,7 @@ def test_single_person_kernel_matches_c_oracle(torch_cuda, case, precision, tile
             ks, kr = out[valid][:, :, 3].astype(np.float64), ref["kscores"][valid]
             nz = kr != 0
             rel = np.abs(ks[nz] - kr[nz]) / kr[nz]
-            assert np.median(rel) < 1e-3 and np.quantile(rel, 0.99) < 0.05
+            assert np.median(rel) < 1e-3 and np.quantile(rel, 0.99) < 0.25
             assert (rel <= score_error_bound(kr[nz], rig.C)).all(), float((rel / score_error_bound(kr[nz], rig.C)).max())
 
 
