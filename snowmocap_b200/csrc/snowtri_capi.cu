@@ -386,7 +386,7 @@ extern "C" int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_sco
     if (((uintptr_t)d_kpts & 7u) != 0) return fail(h, SNOWTRI_E_ARG, "snowtri_run: d_kpts must be 8-byte aligned");
     CUDA_TRY(h, cudaSetDevice(h->device));
 
-    if (snowtri_p1_eligible(h, P, Pout))
+    if (snowtri_p1_eligible(h, P, Pout, keypoint_num))
         return snowtri_p1_run(h, d_kpts, d_scores, d_counts, F, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);
     if (snowtri_general_eligible(h))
         return snowtri_general_run(h, d_kpts, d_scores, d_counts, F, P, J, keypoint_num, Pout, d_out, d_pscores, d_nout, stream);

@@ -28,10 +28,12 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
     a.kpts = g.kpts; a.scores = g.scores; a.out = g.out; a.pscores = g.pscores; a.nout = g.nout;
     a.kcount = g.kcount; a.desc = desc; a.memb2 = memb2;
     a.F = g.F; a.P = g.P; a.J = g.J; a.Jout = g.Jout; a.Pout = g.Pout; a.ncand = g.ncand;
-    // frames per tile: about a thousand (row, joint) items (few idle lanes in the last step), at most 32 rows
+    // frames per tile: about five hundred (row, joint) items, at most 32 rows.  Measured at BASELINE configs[2] (4 of 8
+    // rows filled, 133 joints): 1 frame per tile 0.754 ms, 2 frames 0.840 ms, 4 frames 0.952 ms (profiles/r2g) -- small
+    // tiles balance better over the persistent warps than the few idle lanes of a tile's last step cost.
     {
         const int rows = g.Pout / 2 > 0 ? g.Pout / 2 : 1;
-        int gw = (1024 + rows * g.Jout - 1) / (rows * g.Jout);
+        int gw = (512 + rows * g.Jout - 1) / (rows * g.Jout);
         const int cap = 32 / g.Pout < 1 ? 1 : 32 / g.Pout;
         a.Gw = gw < 1 ? 1 : (gw > cap ? cap : gw);
     }
@@ -73,17 +75,19 @@ static int mfuse_launch(snowtri_t* h, const GenArgs& g, const uint2* memb2, cons
     const char* env = getenv("SNOWTRI_MF_ROLLED");
     const bool rolled = env ? atoi(env) != 0 : false;   // measured at 8 cameras: unrolled 0.82 ms, rolled 1.15 ms (profiles/r2b)
     auto kern = rolled ? mfuse_kernel<C, NT, MINB, true> : mfuse_kernel<C, NT, MINB, false>;
-    const size_t smem = (size_t)(NT / 32) * mfuse_warp_bytes<C>();
+    constexpr int nt = NT;   // 128-thread CTAs, three per SM: 0.820 vs 0.840 ms at 8 cameras (profiles/r2g) -- not kept
+    if (const char* e2 = getenv("SNOWTRI_MF_GW")) a.Gw = atoi(e2) > 0 && atoi(e2) * g.Pout <= 32 ? atoi(e2) : a.Gw;   // experiments
+    const size_t smem = (size_t)(nt / 32) * mfuse_warp_bytes<C>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "mfuse_kernel attribute: %s", cudaGetErrorString(e));
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, nt, smem);
     if (occ < 1) occ = 1;
     int grid = h->sm_count * occ;  // persistent warps fetch tiles from a counter; a short batch uses fewer CTAs
     const long long tiles = ((long long)g.F + a.Gw - 1) / a.Gw;
-    if ((long long)grid * (NT / 32) > tiles) grid = (int)((tiles + NT / 32 - 1) / (NT / 32));
+    if ((long long)grid * (nt / 32) > tiles) grid = (int)((tiles + nt / 32 - 1) / (nt / 32));
     if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
-    kern<<<grid, NT, smem, st>>>(a);
+    kern<<<grid, nt, smem, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "mfuse_kernel launch failed: %s", cudaGetErrorString(e));
     return SNOWTRI_OK;
@@ -190,14 +194,11 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
             // frames that do not fit in shared memory)
             const int mitems = a.npairs * tpp * tpp;  // (camera pair, 4 x 4 person tile) per frame
             if (match_smem) {
-                // warps per CTA: as many as divide the frame's items evenly (<= 7: two CTAs per SM at 146 registers)
-                int nw = 7;
-                double best = 0.0;
-                for (int w = 7; w >= 4; --w) {
-                    const double eff = (double)mitems / (double)(((mitems + w - 1) / w) * w);
-                    if (eff > best + 1e-9) { best = eff; nw = w; }
-                }
-                if (mitems < 4) nw = mitems < 1 ? 1 : mitems;
+                // eight warps per CTA, two CTAs per SM (128 registers).  Measured at BASELINE configs[2] (28 items per
+                // frame): 8 warps 1.10 ms, 7 warps (divides the items evenly) 1.20 ms, 6 warps 1.22 ms, 4 warps 1.41 ms
+                // (profiles/r2g) -- the ray build and the decisions scale with the warps, the idle half round does not hurt.
+                int nw = mitems < 8 ? (mitems < 1 ? 1 : mitems) : 8;
+                if (const char* e4 = getenv("SNOWTRI_MATCH_NW")) nw = atoi(e4) >= 1 && atoi(e4) <= 8 ? atoi(e4) : nw;   // experiments
                 cudaError_t e = cudaFuncSetAttribute(gen_match_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                      (int)(mstaged > 49152 ? mstaged : 49152));
                 if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "gen_match_smem_kernel attribute: %s", cudaGetErrorString(e));

@@ -88,6 +88,6 @@ void snowtri_jit_free(snowtri_t* h);
 #endif
 
 // single-person path (snowtri_p1.cu)
-bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout);
+bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout, int keypoint_num);
 int snowtri_p1_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,
                    int keypoint_num, int Pout, float* d_out, float* d_pscores, int* d_nout, void* stream);

@@ -261,7 +261,7 @@ struct MatchTables {
 // Frames whose rays fit in shared memory (20 bytes per ray): one CTA per frame builds them once and its warps walk the
 // (camera pair, tile) items out of shared memory.  Two CTAs per SM: one CTA's ray build (global loads) and decisions
 // overlap the other's arithmetic.
-__global__ void __launch_bounds__(224, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
+__global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_constant__ GenArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
     MatchTables tb(smem, a);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;

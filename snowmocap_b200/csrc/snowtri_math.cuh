@@ -257,6 +257,18 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ---- mbarrier + 1-D bulk async copy (TMA) -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 4- and 8-byte asynchronous global->shared copies (LDGSTS): a lane's next inputs travel while the current ones are
+// solved, without holding registers; wait_all makes the thread's own copies visible to itself
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) { cp_async4(smem_u32(dst), src); }
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) { cp_async8(smem_u32(dst), src); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

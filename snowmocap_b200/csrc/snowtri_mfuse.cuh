@@ -92,16 +92,6 @@ __device__ __noinline__ float4 mf_item_members(const MFArgs<C>& a, const float2*
     return make_float4(X * rS, Y * rS, Z * rS, S * 0.0005f * rcp_t((float)n));  // S/n, zero-score members counted (Q6)
 }
 
-// 4- and 8-byte asynchronous global->shared copies (LDGSTS): the next item's inputs travel while the current item is
-// solved, without holding registers
-__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
 // per-warp shared memory of mfuse_kernel: row table (32 x 24 B), person-score columns (32 x 33 floats), input stage
 template <int C>
 __host__ __device__ constexpr size_t mfuse_warp_bytes() { return 32 * 24 + 32 * 33 * 4 + (size_t)C * 32 * 12; }

@@ -10,6 +10,14 @@
 #include "snowtri_internal.h"
 #include "snowtri_p1.cuh"
 
+// defaults of the rig-specialised all-float32 build for up to 4 cameras (see the measurements in DESIGN.md)
+#ifndef P1_JIT_DEFAULT_NI
+#define P1_JIT_DEFAULT_NI 2
+#endif
+#ifndef P1_JIT_DEFAULT_MINB
+#define P1_JIT_DEFAULT_MINB 2
+#endif
+
 using namespace snowtri;
 
 // ---- single-person path (snowtri_p1.cuh) -------------------------------------------------------
@@ -34,6 +42,7 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
     a.kpts = d_kpts; a.scores = d_scores; a.counts = d_counts;
     a.out = d_out; a.pscores = d_pscores; a.nout = d_nout;
     a.F = F; a.J = J; a.Jout = keypoint_num; a.Pout = Pout;
+    a.jmagic = p1_div_magic(keypoint_num);
     a.center = h->prm.center; a.num_tol = h->prm.num_tol; a.kst_f = h->prm.kst_f;
     const double inv = h->prm.dthr > 0.0 ? 1.0 / h->prm.dthr : (double)INFINITY;
     a.inv_dthr = (T)inv;
@@ -76,48 +85,51 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
                 }
         }
     auto kern = p1_kernel<T, TD, C, NT>;
-    int occ = 0;
-    auto smem_of = [&](int gw) -> size_t { return (size_t)NW * ((size_t)gw * NP * 24 + (((size_t)gw * 33 * 4 + 7) & ~(size_t)7) + (((size_t)gw * Pout * 4 + 7) & ~(size_t)7)); };
-    // frames per warp tile: few wasted lanes in the last 32-item step, enough tiles to fill every warp slot
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8) > 49152 ? (int)smem_of(8) : 49152) != cudaSuccess)
-        cudaGetLastError();
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_of(8));
-    if (occ < 1) occ = 1;
-    // frames per warp tile: few wasted lanes in the last 32-item step and in the centre step, not longer
-    // than the contiguous frame range a warp owns
-    const long long slots = (long long)h->sm_count * occ * NW;
-    const long long range = ((long long)F + slots - 1) / slots;
-    int Gw = 1;
-    double best = -1.0;
-    for (int gw = 32; gw >= 1; gw >>= 1) {
-        if (gw > 8 && smem_of(gw) * occ > (size_t)h->smem_per_sm - 4096) continue;
-        if (gw > 1 && gw > range) continue;
-        const long long items = (long long)gw * keypoint_num;
-        const double eff = (double)items / (double)((items + 31) / 32 * 32);
-        const double centre = (double)(gw * NP) / (double)((gw * NP + 31) / 32 * 32);  // lanes busy in the centre step
-        const double score = eff * (0.9 + 0.1 * centre);
-        if (score > best + 1e-9) { best = score; Gw = gw; }
-    }
-    if (h->tune_G > 0) Gw = h->tune_G > 32 ? 32 : h->tune_G;
-    a.Gw = Gw;
-    const size_t smem = smem_of(Gw);
-    if (smem > (size_t)h->max_smem)
-        return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_run: single-person path needs %zu B of shared memory (Pout=%d)", smem, Pout);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
-    if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel attribute: %s", cudaGetErrorString(e));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
-    if (occ < 1) occ = 1;
-    int grid = h->sm_count * occ;               // one frame range per warp; a short batch uses fewer CTAs
-    if ((long long)grid * NW > F) grid = (F + NW - 1) / NW;
-    if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+    int ni = P1_NI;  // items per lane of the kernel being launched (the rig-specialised build may use two)
+    auto smem_of = [&](int gw) -> size_t { return (size_t)NW * (size_t)p1_warp_bytes(C, ni, gw, Pout) + (sizeof(TD) != sizeof(T) ? NP * 80 : 0); };
+    // frames per warp tile for `occ` resident CTAs per SM: few wasted lanes in the last step and in the centre step,
+    // not longer than the contiguous frame range a warp owns, and the shared memory of all resident CTAs must fit
+    auto choose_gw = [&](int occ) -> int {
+        const long long slots = (long long)h->sm_count * occ * NW;
+        const long long range = ((long long)F + slots - 1) / slots;
+        int Gw = 1;
+        double best = -1.0;
+        for (int gw = 32; gw >= 1; gw >>= 1) {
+            if (gw > 1 && smem_of(gw) * occ > (size_t)h->smem_per_sm - 1024 * (size_t)occ) continue;
+            if (gw > 1 && gw > range) continue;
+            const long long items = (long long)gw * keypoint_num;
+            const double eff = (double)items / (double)((items + 31) / 32 * 32);
+            const double centre = (double)(gw * NP) / (double)((gw * NP + 31) / 32 * 32);  // lanes busy in the centre step
+            const double score = eff * (0.9 + 0.1 * centre);
+            if (score > best + 1e-9) { best = score; Gw = gw; }
+        }
+        if (h->tune_G > 0) {   // tests: a forced tile size, as far as one CTA's shared memory goes
+            Gw = h->tune_G > 32 ? 32 : h->tune_G;
+            while (Gw > 1 && smem_of(Gw) > (size_t)h->max_smem) Gw >>= 1;
+        }
+        return Gw;
+    };
+    auto grid_of = [&](int occ) -> int {
+        int grid = h->sm_count * occ;               // one frame range per warp; a short batch uses fewer CTAs
+        if ((long long)grid * NW > F) grid = (F + NW - 1) / NW;
+        if (h->tune_ctas > 0 && grid > h->tune_ctas) grid = h->tune_ctas;
+        return grid < 1 ? 1 : grid;
+    };
     // Rig-specialised kernel (float modes): constants and batch shape baked in by NVRTC.  Soft failure.
     if (sizeof(T) == 4 && h->jit_mode > 0 && NT == 256) {
         char buf[256];
         std::string src = "#define P1_JIT 1\n";
-        // with the constants out of the register file, two items per lane per step pay off in all-float32
-        // (measured at cfg2: 0.608 -> 0.640 of the HBM roof; in mixed mode the float64 rays make it spill)
-        if (sizeof(TD) == 4 && C <= 4) src += "#define P1_NI 2\n";
-        if (const char* extra = getenv("SNOWTRI_JIT_DEFINES")) {  // experiments: "P1_NI=2 P1_L2_AHEAD=1"
+        // Items per lane and resident CTAs per SM of the specialised build.  With the constants out of the register
+        // file and the next step's inputs staged through shared memory (no prefetch registers), two items per lane
+        // side by side (twice the independent dependency chains, constants materialised once per pair) fit in 128
+        // registers in both float modes.  Measured at BASELINE configs[1], ms per 131 072 frames (profiles/r2l, r2m):
+        //   all-float32: 2 items x 2 CTAs 0.249 | 1 x 2: 0.274 | 1 x 3 (80 registers): 0.280 | 1 x 4: 0.304 | 2 x 3: 0.415 (spills)
+        //   mixed:       2 x 2: 0.305 | 1 x 2: 0.315 | 1 x 3: 0.402 | 1 x 1: 0.394
+        // More resident warps do not help: the issue rate saturates near 0.75-0.8 per scheduler either way.
+        ni = C <= 4 ? P1_JIT_DEFAULT_NI : 1;
+        int minb = C <= 4 ? P1_JIT_DEFAULT_MINB : p1_min_blocks<T, TD, C>();
+        if (const char* e = getenv("SNOWTRI_JIT_MINB")) minb = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : minb;   // experiments
+        if (const char* extra = getenv("SNOWTRI_JIT_DEFINES")) {  // experiments: "P1_NI=2 OTHER=1"
             std::string e(extra);
             size_t pos = 0;
             while (pos < e.size()) {
@@ -125,10 +137,16 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
                 if (sp == std::string::npos) sp = e.size();
                 std::string tok = e.substr(pos, sp - pos);
                 const size_t eq = tok.find('=');
-                if (!tok.empty()) src += "#define " + (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) + "\n";
+                if (tok.compare(0, 6, "P1_NI=") == 0) ni = atoi(tok.c_str() + 6) == 2 ? 2 : 1;
+                else if (!tok.empty()) src += "#define " + (eq == std::string::npos ? tok : tok.substr(0, eq) + " " + tok.substr(eq + 1)) + "\n";
                 pos = sp + 1;
             }
         }
+        snprintf(buf, sizeof(buf), "#define P1_NI %d\n", ni);
+        src += buf;
+        const int Gw = choose_gw(minb);
+        const size_t smem = smem_of(Gw);
+        a.Gw = Gw;
         auto def_i = [&](const char* n, int v) { snprintf(buf, sizeof(buf), "#define %s %d\n", n, v); src += buf; };
         auto def_f = [&](const char* n, float v) {
             if (isinf(v)) snprintf(buf, sizeof(buf), "#define %s __int_as_float(0x7f800000)\n", n);
@@ -148,11 +166,11 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
         snprintf(buf, sizeof(buf),
                  "#include \"snowtri_p1.cuh\"\nextern \"C\" __global__ void __launch_bounds__(256, %d) p1_jit("
                  "const __grid_constant__ snowtri::P1Args<float, %d> a) { snowtri::p1_body<float, %s, %d, 256>(a); }\n",
-                 getenv("SNOWTRI_JIT_MINB") ? atoi(getenv("SNOWTRI_JIT_MINB")) : p1_min_blocks<T, TD, C>(), C,
-                 sizeof(TD) == 8 ? "double" : "float", C);
+                 minb, C, sizeof(TD) == 8 ? "double" : "float", C);
         src += buf;
-        if (h->jit_mode == 2 || F >= 65536 || snowtri_jit_cached(h, src)) {
+        if (smem <= (size_t)h->max_smem && (h->jit_mode == 2 || F >= 65536 || snowtri_jit_cached(h, src))) {
             if (void* fn = snowtri_jit_get(h, src, "p1_jit", smem)) {
+                const int grid = grid_of(minb);
                 const int rc = snowtri_jit_launch(fn, grid, NT, smem, stream, &a);
                 if (rc == 0) {
                     h->launches += 1;
@@ -164,6 +182,23 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
             }
         }
     }
+    // precompiled kernel
+    ni = P1_NI;
+    int occ = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_of(8) > 49152 ? (int)smem_of(8) : 49152) != cudaSuccess)
+        cudaGetLastError();
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem_of(8));
+    if (occ < 1) occ = 1;
+    const int Gw = choose_gw(occ);
+    a.Gw = Gw;
+    const size_t smem = smem_of(Gw);
+    if (smem > (size_t)h->max_smem)
+        return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_run: single-person path needs %zu B of shared memory (Pout=%d)", smem, Pout);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem > 49152 ? smem : 49152));
+    if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel attribute: %s", cudaGetErrorString(e));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem);
+    if (occ < 1) occ = 1;
+    const int grid = grid_of(occ);
     kern<<<grid, NT, smem, (cudaStream_t)stream>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "p1_kernel launch failed: %s", cudaGetErrorString(e));
@@ -190,10 +225,10 @@ static int run_p1(snowtri_t* h, const float* d_kpts, const float* d_scores, cons
 }
 
 
-bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout) {
+bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout, int keypoint_num) {
     const bool all_kept = h->prm.ast <= 0.0 && h->prm.kst >= 0.0;
     const bool never_filter = h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0;
-    return !h->no_p1 && P == 1 && h->C >= 2 && h->C <= 8 && all_kept && never_filter && Pout <= 64;
+    return !h->no_p1 && P == 1 && h->C >= 2 && h->C <= 8 && all_kept && never_filter && Pout <= 64 && keypoint_num <= kP1MaxJout;
 }
 
 int snowtri_p1_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,

@@ -6,8 +6,8 @@
 //     only synchronisation is __syncwarp(), so no CTA barrier ever stalls the FP pipes;
 //   * lanes run over the flattened (frame, joint) index of the tile: 32 consecutive joints of one
 //     camera row are one coalesced 256-byte read, and a tile of Gw*J items wastes < 32 lanes;
-//     the (u,v,score) of the NEXT item are loaded into registers before the current one is solved,
-//     so HBM latency is hidden by the ~400 instructions of an item and not by occupancy;
+//     the (u,v,score) of the NEXT step are copied to shared memory with cp.async before the current
+//     step is solved, so HBM latency is hidden by the ~700 instructions of a step and not by occupancy;
 //   * with one person per camera a candidate IS a camera pair, so a cluster is a bit mask over the
 //     C(C-1)/2 pairs.  The greedy clustering (reference triangulation.py:107-134) runs per frame in
 //     one lane on bit masks; the fuse (reference :138-148) is a fully unrolled loop over the pairs
@@ -16,9 +16,13 @@
 //   * the rays of a joint are built once in registers and shared by all pairs;
 //   * sum(score * point) is accumulated as  sum(w*mid) + 1/2 * sum_c alpha_c * h_c  with one scalar
 //     alpha per camera instead of a 3-vector per pair (see snowtri_math.cuh for the algebra);
-//   * the person score (mean keypoint score, reference :150) is accumulated in registers per lane,
-//     parked in a per-warp shared-memory column when the lane crosses a frame boundary and added up in a
-//     fixed order by one lane per frame: deterministic, no atomics, no re-read of the output.
+//   * the item loop carries no (frame, joint) bookkeeping: an item's frame is one multiply-high of its flat index,
+//     and a tile whose frames all hold the full clique (one vote per tile) never looks at the masks;
+//   * the person score (mean keypoint score, reference :150) is accumulated in registers per lane; whenever a step
+//     contains the end of a frame -- a warp-uniform test, so a step without a frame end spends one add per item on
+//     it -- the lanes' sums are added up by a fixed-order warp shuffle: deterministic, no atomics, no shared memory,
+//     no re-read of the output.  (Reading the scores back at the end of a tile was tried: a warp's tile lives for
+//     the whole launch, the rows are long gone from L2, +25 % DRAM reads.)
 //
 // Precision (template T = bulk arithmetic, TD = arithmetic of the ray-distance numerator d.(hm x hs)):
 //   <double,double>  everything in float64, like the reference.
@@ -52,6 +56,10 @@ template <int V>
 struct IntC {
     static constexpr int value = V;
 };
+template <bool V>
+struct BoolC {
+    static constexpr bool value = V;
+};
 template <int C, int X = 0, int Y = 1, typename F>
 __device__ __forceinline__ void static_for_pairs(F&& f) {
     if constexpr (X < C - 1) {
@@ -71,6 +79,7 @@ struct P1Args {
     float* pscores;       // (F,Pout)
     int* nout;            // (F)
     int F, J, Jout, Pout, Gw, center, num_tol;
+    uint32_t jmagic;       // p1_div_magic(Jout)
     float kst_f;
     T inv_dthr;
     float guard_w;         // float modes: re-decide in float64 when |1/dist - 1/dthr| < guard_w (0 = never)
@@ -138,8 +147,8 @@ __device__ __noinline__ float4 p1_item_exact(const P1Args<T, C>& a, const float2
 #ifndef P1_KEEP
 #define P1_KEEP 1
 #endif
-#ifndef P1_L2_AHEAD
-#define P1_L2_AHEAD 0   // per-lane L2 prefetch this many steps beyond the register prefetch (0 = off)
+#ifndef P1_E64_SMEM
+#define P1_E64_SMEM 1   // mixed mode: float64 pair constants read from shared memory inside the loop
 #endif
 #ifndef P1_NI
 #define P1_NI 1   // items a lane solves side by side per step (1 or 2)
@@ -167,6 +176,29 @@ constexpr int p1_min_blocks() {
 #endif
 }
 
+// floor(q / d) for 0 <= q < 2^32 / d with magic = ceil(2^32 / d): one IMAD.HI instead of a running (frame, joint) pair
+__host__ __device__ constexpr uint32_t p1_div_magic(int d) { return (uint32_t)((0x100000000ull + (uint32_t)d - 1u) / (uint32_t)d); }
+constexpr int kP1MaxJout = 8192;  // 32 * Jout * Jout < 2^32 keeps the magic division exact over a tile
+
+// Staging of the next step's inputs: every lane copies the (u, v) and the score of its own next items from global to
+// shared memory with cp.async (LDGSTS: no destination registers, so nothing tempts the compiler to sink the loads
+// behind the pair solves -- with register loads ptxas did exactly that and the step no longer covered the memory
+// latency, profiles/r2h) and reads them back one step later.  A lane's record holds its C float2 and C scores; the
+// record stride is 8 bytes times an odd number, which makes the 64-bit copies and the 64-bit reads conflict-free (a
+// 48-byte stride with 128-bit reads made the copies 4-way conflicted: 15 M conflict cycles per launch, profiles/r2j).
+__host__ __device__ constexpr int p1_rec_bytes(int C) {
+    const int r = (C * 12 + 7) / 8 * 8;
+    return (r / 8) % 2 ? r : r + 8;
+}
+__host__ __device__ constexpr int p1_stage_bytes(int C, int NI) { return NI * 32 * p1_rec_bytes(C); }
+// per-warp shared memory: [centres | stage 1] [stage 0] [cluster masks].  Kept small on purpose: what the CTAs of an SM
+// do not claim stays L1, and the copies in flight need their lines there -- 2 x 94 KB per SM left 60 KB of L1 and ran at
+// 0.247 ms per 131 072 frames, 2 x 98 KB tipped the carve-out to 228 KB (28 KB of L1): 0.338 ms (profiles/r2j, r2k).
+__host__ __device__ constexpr int p1_warp_bytes(int C, int NI, int Gw, int Pout) {
+    const int NP = C * (C - 1) / 2;
+    const int cen = Gw * NP * 24, stg = p1_stage_bytes(C, NI);
+    return (((cen > stg ? cen : stg) + 15) / 16 * 16 + stg + ((Gw * Pout * 4 + 7) & ~7) + 15) / 16 * 16;
+}
 template <typename T, typename TD, int C, int NT>
 __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
     constexpr int NP = C * (C - 1) / 2;
@@ -174,28 +206,46 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
     constexpr unsigned ALL = (NP >= 32) ? 0xffffffffu : ((1u << NP) - 1u);
     constexpr bool MIXED = sizeof(TD) != sizeof(T);
     constexpr int NI = P1_NI;
+    constexpr int STEP = 32 * NI;
+    constexpr int REC = p1_rec_bytes(C), STG = p1_stage_bytes(C, NI);
     extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #ifdef P1_JIT
     constexpr int J = P1_JIT_J, Jout = P1_JIT_JOUT, Pout = P1_JIT_POUT, Gw = P1_JIT_GW;
     constexpr float kst_f = P1_JIT_KST, guard_w = P1_JIT_GUARD_W;
     constexpr T inv_dthr = (T)P1_JIT_INV_DTHR, kscale_full = (T)P1_JIT_KSCALE_FULL;
+    constexpr uint32_t jmagic = p1_div_magic(P1_JIT_JOUT);
 #else
     const int J = a.J, Jout = a.Jout, Pout = a.Pout, Gw = a.Gw;
     const float kst_f = a.kst_f, guard_w = a.guard_w;
     const T inv_dthr = a.inv_dthr, kscale_full = a.kscale[NP];
+    const uint32_t jmagic = a.jmagic;
 #endif
-    // per-warp scratch: centres (Gw*NP*3 doubles), person-score columns (Gw*32 floats), cluster masks (Gw*Pout words)
-    const int warp_bytes = Gw * NP * 24 + ((Gw * 33 * 4 + 7) & ~7) + ((Gw * Pout * 4 + 7) & ~7);
-    double* cen = reinterpret_cast<double*>(smem + (size_t)warp * warp_bytes);
-    float* part = reinterpret_cast<float*>(cen + Gw * NP * 3);
-    uint32_t* meta = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(part) + ((Gw * 33 * 4 + 7) & ~7));
+    // per-warp scratch (p1_warp_bytes): the centres (Gw*NP*3 doubles) are dead once the tile is clustered, so the
+    // second staging buffer lives on top of them
+    unsigned char* wbase = smem + (size_t)warp * p1_warp_bytes(C, NI, Gw, Pout);
+    const int cen_bytes = (max(Gw * NP * 24, STG) + 15) / 16 * 16;
+    double* cen = reinterpret_cast<double*>(wbase);
+    unsigned char* stage1 = wbase;
+    unsigned char* stage0 = wbase + cen_bytes;
+    uint32_t* meta = reinterpret_cast<uint32_t*>(stage0 + STG);
+#if P1_E64_SMEM
+    uint32_t e64s = 0;  // mixed mode: the pairs' float64 epipolar forms, one copy per CTA behind the warps' scratch
+    if constexpr (MIXED) {
+        double* e64 = reinterpret_cast<double*>(smem + (size_t)NW * p1_warp_bytes(C, NI, Gw, Pout));
+        for (int i = threadIdx.x; i < NP * 10; i += NT) e64[i] = a.E64[i];
+        __syncthreads();
+        e64s = smem_u32(e64);
+    }
+#endif
 
     const float2* kp2 = reinterpret_cast<const float2*>(a.kpts);
     const int CJ = C * J;
+    const int in_skip = CJ - Jout;            // item q = g*Jout + j reads input element g*CJ + j = q + g*in_skip
+    const int out_skip = (Pout - 1) * Jout;   // ... and writes output row (g*Pout)*Jout + j = q + g*out_skip
     // Each warp owns one contiguous range of frames and walks it tile by tile: its input is two
-    // sequential streams (kpts, scores).  (An explicit L2 look-ahead with cp.async.bulk.prefetch.L2 was
-    // measured and made the kernel 8-10 % slower; the register prefetch of the next item is enough.)
+    // sequential streams (kpts, scores).  (An explicit L2 look-ahead with cp.async.bulk.prefetch.L2 or per-lane
+    // prefetch.global.L2 was measured and made the kernel 4-10 % slower; one step of look-ahead is enough.)
     const int gwarp = blockIdx.x * NW + warp, nwarps = gridDim.x * NW;
     const int fa = (int)((long long)a.F * gwarp / nwarps), fb = (int)((long long)a.F * (gwarp + 1) / nwarps);
     T m2[C][3];  // constant addends of the rays (third column of M): an FFMA takes one constant-bank operand only
@@ -204,7 +254,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             m2[c][k] = P1_CAMC(T, 12 * c + 4 * k + 2);
-#if P1_KEEP
+#if P1_KEEP && !defined(P1_JIT)
             keep_in_register(m2[c][k]);
 #endif
         }
@@ -212,6 +262,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
     for (int f0 = fa; f0 < fb; f0 += Gw) {
         const int Gc = min(Gw, fb - f0);
         const int nitems = Gc * Jout;
+        const int nsteps = (nitems + STEP - 1) / STEP;  // in the last one the lanes past the end redo the last item and store nothing
         const float2* kpt = kp2 + (size_t)f0 * CJ;
         const float* sct = a.scores + (size_t)f0 * CJ;
         const float2* kpc[C];  // per-camera rows of the tile: one 64-bit add per load in the item loop
@@ -220,57 +271,29 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
         for (int c = 0; c < C; ++c) {
             kpc[c] = kpt + c * J;
             scc[c] = sct + c * J;
-#if P1_KEEP
+#if P1_KEEP && !defined(P1_JIT)
             keep_in_register(kpc[c]);
             keep_in_register(scc[c]);
 #endif
         }
         float4* outt = reinterpret_cast<float4*>(a.out) + (size_t)f0 * Pout * Jout;
 
-        // (frame, joint) of this lane's first NI items (item u of a step is 32*u further); lanes past the
-        // end redo the last item and store nothing
-        auto advance = [&](int& gg, int& jj) {  // 32 items further
-            jj += 32;
-            if (Jout >= 32) {  // at most one frame boundary
-                if (jj >= Jout) {
-                    jj -= Jout;
-                    ++gg;
-                }
-            } else {
-                while (jj >= Jout) {
-                    jj -= Jout;
-                    ++gg;
+        // the inputs of the NI items of this lane in the step that starts at item q0: global -> this lane's records
+        auto stage_in = [&](unsigned char* stage, uint32_t q0) {
+            const uint32_t rec = smem_u32(stage) + lane * REC;
+#pragma unroll
+            for (int u = 0; u < NI; ++u) {
+                const uint32_t q = min(q0 + 32 * u + lane, (uint32_t)nitems - 1u);
+                const uint32_t off = q + __umulhi(q, jmagic) * (uint32_t)in_skip;  // unsigned: stays 32-bit arithmetic
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    cp_async8(rec + u * 32 * REC + c * 8, kpc[c] + off);
+                    cp_async4(rec + u * 32 * REC + C * 8 + c * 4, scc[c] + off);
                 }
             }
         };
-        int g[NI], j[NI];
-        g[0] = 0;
-        j[0] = lane - 32;
-        advance(g[0], j[0]);
-#pragma unroll
-        for (int u = 1; u < NI; ++u) {
-            g[u] = g[u - 1];
-            j[u] = j[u - 1];
-            advance(g[u], j[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < NI; ++u)
-            if (32 * u + lane >= nitems) {
-                g[u] = Gc - 1;
-                j[u] = Jout - 1;
-            }
-        // ---- first items' inputs: in flight while the tile's clustering runs ---------------------------
-        float2 p2n[NI][C];
-        float s1n[NI][C];
-#pragma unroll
-        for (int u = 0; u < NI; ++u) {
-            const int off = g[u] * CJ + j[u];
-#pragma unroll
-            for (int c = 0; c < C; ++c) {
-                p2n[u][c] = __ldg(kpc[c] + off);
-                s1n[u][c] = __ldg(scc[c] + off);
-            }
-        }
+        // ---- first step's inputs: in flight while the tile's clustering runs ---------------------------
+        stage_in(stage0, 0u);
 
         // ---- centre-joint midpoint of every candidate, float64 (reference triangulation.py:112,124) ----
         for (int idx = lane; idx < Gc * NP; idx += 32) {
@@ -289,11 +312,11 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
             cen[3 * idx + 1] = w.y;
             cen[3 * idx + 2] = w.z;
         }
-        for (int gg = 0; gg < Gc; ++gg) part[gg * 33 + lane] = 0.f;
         __syncwarp();
 
         // ---- greedy clustering on pair bit masks, one lane per frame (reference :107-134) ----------
         int K = 0;
+        unsigned mask0 = ALL;  // slot 0 of this lane's frame (lanes beyond the tile: neutral)
         if (lane < Gc) {
             unsigned present = (1u << C) - 1u;
             if (a.counts) {
@@ -307,6 +330,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
 #pragma unroll
                 for (int y = x + 1; y < C; ++y)
                     if ((present >> x) & (present >> y) & 1u) valid |= 1u << pair_index(C, x, y);
+            mask0 = 0u;
             if (valid) {
                 const int last = 31 - __clz(valid);
                 unsigned mains = valid & ~(1u << last);  // the last candidate is never a main (Q1/Q2)
@@ -330,6 +354,7 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                     }
                     if (__popc(mask) >= a.num_tol) {  // otherwise its members stay absorbed (Q5)
                         if (K < Pout) meta[lane * Pout + K] = mask;
+                        if (K == 0) mask0 = mask;
                         ++K;
                     }
                 }
@@ -338,147 +363,141 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
             a.nout[f0 + lane] = K;
         }
         const bool multi = __any_sync(kFullMask, K > 1) && Pout > 1;  // some frame has a second cluster
-        __syncwarp();
+        const bool tile_full = __all_sync(kFullMask, mask0 == ALL);    // every frame's first cluster is the full clique
+        __syncwarp();  // the centres are dead from here on: stage 1 may overwrite them
 
         // ---- fuse: lanes over the flattened (frame, joint) index of the tile ---------------------------
         // A step covers 32*NI consecutive items; a lane solves NI of them side by side (independent
-        // dependency chains, constants fetched once per pair).
-        float acc = 0.f;  // this lane's share of the person score of frame `gacc`
-        int gacc = g[0];
-        for (int q0 = 0; q0 < nitems; q0 += 32 * NI) {
-            V3<T> h[NI][C];
-            TD ud[NI][MIXED ? C : 1], vd[NI][MIXED ? C : 1];  // mixed: pixel coordinates in float64
-            T A[NI][C], sc[NI][C];
-            int off[NI];
-            bool live[NI];
+        // dependency chains, constants fetched once per pair).  TF: the whole tile is known to be full cliques,
+        // so the loop neither looks at the masks nor votes.
+        // Person score (mean keypoint score, reference :150): a lane adds up the scores of its items; when a step
+        // contains the end of a frame (a warp-uniform test, at most one per step when Jout >= 32*NI) the warp adds up
+        // the lanes' sums in a fixed order and lane 0 stores the frame's score.  No shared memory, no atomics.
+        float acc = 0.f;
+        auto run_steps = [&](auto tfc) {
+            constexpr bool TF = decltype(tfc)::value;
+            for (int st = 0; st < nsteps; ++st) {
+                const int qb = st * STEP + lane;  // this lane's first item of the step
+                V3<T> h[NI][C];
+                TD ud[NI][MIXED ? C : 1], vd[NI][MIXED ? C : 1];  // mixed: pixel coordinates in float64
+                T A[NI][C], sc[NI][C];
+                cp_async_wait_all();  // this lane's records of the step (written by its own copies)
+                // next step's items of this lane: copies issued first thing (into the buffer that was last read one
+                // step ago), read one step later -- a whole step of arithmetic covers the memory latency
+                if (st + 1 < nsteps) stage_in((st & 1) ? stage0 : stage1, (uint32_t)(st + 1) * STEP);
+                {
+                    const unsigned char* rec = ((st & 1) ? stage1 : stage0) + lane * REC;
 #pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                live[u] = q0 + 32 * u + lane < nitems;
-                off[u] = g[u] * CJ + j[u];
+                    for (int u = 0; u < NI; ++u) {
+                        float w[REC / 4];
 #pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    h[u][c].x = fma(P1_CAMC(T, 12 * c + 0), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 1), (T)p2n[u][c].y, m2[c][0]));
-                    h[u][c].y = fma(P1_CAMC(T, 12 * c + 4), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 5), (T)p2n[u][c].y, m2[c][1]));
-                    h[u][c].z = fma(P1_CAMC(T, 12 * c + 8), (T)p2n[u][c].x, fma(P1_CAMC(T, 12 * c + 9), (T)p2n[u][c].y, m2[c][2]));
-                    if constexpr (MIXED) {
-                        ud[u][c] = (TD)p2n[u][c].x;
-                        vd[u][c] = (TD)p2n[u][c].y;
+                        for (int i = 0; i < (C * 12 + 7) / 8; ++i) {
+                            const float2 v = *reinterpret_cast<const float2*>(rec + u * 32 * REC + i * 8);
+                            w[2 * i] = v.x; w[2 * i + 1] = v.y;
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const T pu = (T)w[2 * c], pv = (T)w[2 * c + 1];
+                            h[u][c].x = fma(P1_CAMC(T, 12 * c + 0), pu, fma(P1_CAMC(T, 12 * c + 1), pv, m2[c][0]));
+                            h[u][c].y = fma(P1_CAMC(T, 12 * c + 4), pu, fma(P1_CAMC(T, 12 * c + 5), pv, m2[c][1]));
+                            h[u][c].z = fma(P1_CAMC(T, 12 * c + 8), pu, fma(P1_CAMC(T, 12 * c + 9), pv, m2[c][2]));
+                            if constexpr (MIXED) {
+                                ud[u][c] = (TD)w[2 * c];
+                                vd[u][c] = (TD)w[2 * c + 1];
+                            }
+                            A[u][c] = dot3(h[u][c], h[u][c]);
+                            // a score below the keypoint threshold kills every pair of its camera: poison it so that
+                            // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
+                            sc[u][c] = w[2 * C + c] < kst_f ? (T)-1e30 : (T)w[2 * C + c];
+                        }
                     }
-                    A[u][c] = dot3(h[u][c], h[u][c]);
-                    // a score below the keypoint threshold kills every pair of its camera: poison it so that
-                    // max(sm + ss, 0) is 0 (scores that pass are >= kst >= 0 on this path)
-                    sc[u][c] = s1n[u][c] < kst_f ? (T)-1e30 : (T)s1n[u][c];
                 }
-            }
-            // next items of this lane: issue their loads now, use them one step later
-            int gn[NI], jn[NI];
+                // output slot 0: the unrolled path
+                int gq_[NI];          // frame of the item inside the tile (only looked at when the masks are)
+                unsigned mask[NI];
+                bool full = true;
+                if constexpr (!TF) {
+                    bool allfull = true;
 #pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                gn[u] = g[u];
-                jn[u] = j[u];
+                    for (int u = 0; u < NI; ++u) {
+                        gq_[u] = (int)__umulhi((uint32_t)min(qb + 32 * u, nitems - 1), jmagic);
+                        mask[u] = meta[gq_[u] * Pout];
+                        allfull = allfull && mask[u] == ALL;
+                    }
+                    full = __all_sync(kFullMask, allfull);
+                } else {
 #pragma unroll
-                for (int k = 0; k < NI; ++k) advance(gn[u], jn[u]);
-                if (q0 + 32 * (NI + u) + lane >= nitems) {
-                    gn[u] = Gc - 1;
-                    jn[u] = Jout - 1;
+                    for (int u = 0; u < NI; ++u) {
+                        gq_[u] = 0;
+                        mask[u] = ALL;
+                    }
                 }
-            }
-            if (q0 + 32 * NI < nitems) {
+                T S[NI], Xm[NI], Ym[NI], Zm[NI], al[NI][C];
+                float margin[NI];  // float modes: smallest |1/dist - 1/dthr| over the pairs
 #pragma unroll
                 for (int u = 0; u < NI; ++u) {
-                    const int offn = gn[u] * CJ + jn[u];
+                    S[u] = Xm[u] = Ym[u] = Zm[u] = (T)0;
+                    margin[u] = INFINITY;
 #pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        p2n[u][c] = __ldg(kpc[c] + offn);
-                        s1n[u][c] = __ldg(scc[c] + offn);
-                    }
+                    for (int c = 0; c < C; ++c) al[u][c] = (T)0;
                 }
-            }
-#if P1_L2_AHEAD
-            // the items P1_L2_AHEAD steps further: pull their lines into L2 so that the register loads above
-            // (one step ahead) see L2 latency, not HBM latency
-            if (q0 + 32 * NI * (1 + P1_L2_AHEAD) < nitems) {
-                int gp = gn[NI - 1], jp = jn[NI - 1];
+                auto pair = [&](auto xc, auto yc, auto uc) {
+                    constexpr int x = decltype(xc)::value, y = decltype(yc)::value, u = decltype(uc)::value;
+                    constexpr int e = pair_index(C, x, y);
+                    V3<T> d;
+                    d.x = P1_PDC(T, e * 8); d.y = P1_PDC(T, e * 8 + 1); d.z = P1_PDC(T, e * 8 + 2);
+                    const PairSolN<T> s = pair_solve_n(h[u][x], A[u][x], h[u][y], A[u][y], d);
+                    T dn;
+                    if constexpr (MIXED) {  // l = E [uy vy 1]^T, d.n = [ux vx 1] l
+#if P1_E64_SMEM
+                        // the pair's nine float64 constants from the CTA's shared-memory copy, read where they are
+                        // used: DFMA takes no constant-bank operand on this part, and left to itself the compiler hoists
+                        // the 54 loads out of the loop and shuffles them between register files (profiles/r2l)
+                        double E[10];
 #pragma unroll
-                for (int k = 0; k < NI * P1_L2_AHEAD; ++k) advance(gp, jp);
-                if (gp < Gc) {
-                    const int offp = gp * CJ + jp;
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(kpc[c] + offp));
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(scc[c] + offp));
-                    }
-                }
-            }
+                        for (int i = 0; i < 5; ++i)
+                            asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(E[2 * i]), "=d"(E[2 * i + 1]) : "r"(e64s + (10 * e + 2 * i) * 8));
+#else
+                        const double* E = a.E64 + 10 * e;
 #endif
-
-            // output slot 0: the unrolled path
-            unsigned mask[NI];
-            bool allfull = true;
-#pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                mask[u] = meta[g[u] * Pout];
-                allfull = allfull && mask[u] == ALL;
-            }
-            const bool full = __all_sync(kFullMask, allfull);
-            T S[NI], Xm[NI], Ym[NI], Zm[NI], al[NI][C];
-            float margin[NI];  // float modes: smallest |1/dist - 1/dthr| over the pairs
-#pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                S[u] = Xm[u] = Ym[u] = Zm[u] = (T)0;
-                margin[u] = INFINITY;
-#pragma unroll
-                for (int c = 0; c < C; ++c) al[u][c] = (T)0;
-            }
-            auto pair = [&](auto xc, auto yc, auto uc) {
-                constexpr int x = decltype(xc)::value, y = decltype(yc)::value, u = decltype(uc)::value;
-                constexpr int e = pair_index(C, x, y);
-                V3<T> d;
-                d.x = P1_PDC(T, e * 8); d.y = P1_PDC(T, e * 8 + 1); d.z = P1_PDC(T, e * 8 + 2);
-                const PairSolN<T> s = pair_solve_n(h[u][x], A[u][x], h[u][y], A[u][y], d);
-                T dn;
-                if constexpr (MIXED) {  // l = E [uy vy 1]^T, d.n = [ux vx 1] l
-                    const double* E = a.E64 + 10 * e;
-                    const TD l0 = fma(E[0], ud[u][y], fma(E[1], vd[u][y], E[2]));
-                    const TD l1 = fma(E[3], ud[u][y], fma(E[4], vd[u][y], E[5]));
-                    const TD l2 = fma(E[6], ud[u][y], fma(E[7], vd[u][y], E[8]));
-                    dn = (T)fma(l0, ud[u][x], fma(l1, vd[u][x], l2));
+                        const TD l0 = fma(E[0], ud[u][y], fma(E[1], vd[u][y], E[2]));
+                        const TD l1 = fma(E[3], ud[u][y], fma(E[4], vd[u][y], E[5]));
+                        const TD l2 = fma(E[6], ud[u][y], fma(E[7], vd[u][y], E[8]));
+                        dn = (T)fma(l0, ud[u][x], fma(l1, vd[u][x], l2));
+                    } else {
+                        dn = cross_dot(h[u][x], h[u][y], d);
+                    }
+                    const T r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
+                    const T rd = r * s.det;                   // 1/dist
+                    if constexpr (sizeof(T) == 4) margin[u] = fminf(margin[u], fabsf(rd - inv_dthr));
+                    T gq = fmax(sc[u][x] + sc[u][y], (T)0) * r;
+                    if (rd < inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
+                    const T w = gq * s.det;
+                    S[u] += w;
+                    al[u][x] = fma(gq, s.n0, al[u][x]);
+                    al[u][y] = fma(-gq, s.n1, al[u][y]);
+                    Xm[u] = fma(w, P1_PDC(T, e * 8 + 4), Xm[u]);
+                    Ym[u] = fma(w, P1_PDC(T, e * 8 + 5), Ym[u]);
+                    Zm[u] = fma(w, P1_PDC(T, e * 8 + 6), Zm[u]);
+                };
+                if (full) {
+                    static_for_pairs<C>([&](auto xc, auto yc) {
+                        pair(xc, yc, IntC<0>{});
+                        if constexpr (NI > 1) pair(xc, yc, IntC<NI - 1>{});
+                    });
                 } else {
-                    dn = cross_dot(h[u][x], h[u][y], d);
+                    static_for_pairs<C>([&](auto xc, auto yc) {
+                        constexpr int e = pair_index(C, decltype(xc)::value, decltype(yc)::value);
+                        if ((mask[0] >> e) & 1u) pair(xc, yc, IntC<0>{});
+                        if constexpr (NI > 1)
+                            if ((mask[NI - 1] >> e) & 1u) pair(xc, yc, IntC<NI - 1>{});
+                    });
                 }
-                const T r = rsqrt_fast(s.det * dn * dn);  // q.q = det * (d.n)^2
-                const T rd = r * s.det;                   // 1/dist
-                if constexpr (sizeof(T) == 4) margin[u] = fminf(margin[u], fabsf(rd - inv_dthr));
-                T gq = fmax(sc[u][x] + sc[u][y], (T)0) * r;
-                if (rd < inv_dthr) gq = (T)0;  // dist > dthr (strict); NaN is not gated (Q8/Q9)
-                const T w = gq * s.det;
-                S[u] += w;
-                al[u][x] = fma(gq, s.n0, al[u][x]);
-                al[u][y] = fma(-gq, s.n1, al[u][y]);
-                Xm[u] = fma(w, P1_PDC(T, e * 8 + 4), Xm[u]);
-                Ym[u] = fma(w, P1_PDC(T, e * 8 + 5), Ym[u]);
-                Zm[u] = fma(w, P1_PDC(T, e * 8 + 6), Zm[u]);
-            };
-            if (full) {
-                static_for_pairs<C>([&](auto xc, auto yc) {
-                    pair(xc, yc, IntC<0>{});
-                    if constexpr (NI > 1) pair(xc, yc, IntC<NI - 1>{});
-                });
-            } else {
-                static_for_pairs<C>([&](auto xc, auto yc) {
-                    constexpr int e = pair_index(C, decltype(xc)::value, decltype(yc)::value);
-                    if ((mask[0] >> e) & 1u) pair(xc, yc, IntC<0>{});
-                    if constexpr (NI > 1)
-                        if ((mask[NI - 1] >> e) & 1u) pair(xc, yc, IntC<NI - 1>{});
-                });
-            }
+                float ks[NI];  // keypoint scores of slot 0, for the person score
 #pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (sizeof(T) == 4 && margin[u] < guard_w && mask[u]) {
-                    // a float32 distance within the guard band of dthr: decide in float64
-                    o = p1_item_exact<T, TD, C>(a, kpt + off[u], sct + off[u], mask[u]);
-                } else if (S[u] != (T)0) {  // S == 0 leaves (0,0,0) with score 0 (Q7)
+                for (int u = 0; u < NI; ++u) {
+                    const bool live = qb + 32 * u < nitems;
+                    const int q = min(qb + 32 * u, nitems - 1);
                     T X = (T)0, Y = (T)0, Z = (T)0;
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
@@ -486,63 +505,82 @@ __device__ __forceinline__ void p1_body(const P1Args<T, C>& a) {
                         Y = fma(al[u][c], h[u][c].y, Y);
                         Z = fma(al[u][c], h[u][c].z, Z);
                     }
-                    const T rS = rcp_fast(S[u]);
-                    o.x = (float)(fma((T)0.5, X, Xm[u]) * rS);
-                    o.y = (float)(fma((T)0.5, Y, Ym[u]) * rS);
-                    o.z = (float)(fma((T)0.5, Z, Zm[u]) * rS);
+                    const bool some = S[u] != (T)0;  // S == 0 leaves (0,0,0) with score 0 (Q7)
+                    const T rS = rcp_fast(some ? S[u] : (T)1);
+                    float4 o;
+                    o.x = some ? (float)(fma((T)0.5, X, Xm[u]) * rS) : 0.f;
+                    o.y = some ? (float)(fma((T)0.5, Y, Ym[u]) * rS) : 0.f;
+                    o.z = some ? (float)(fma((T)0.5, Z, Zm[u]) * rS) : 0.f;
                     o.w = (float)(S[u] * (full ? kscale_full : a.kscale[__popc(mask[u])]));
-                }
-                if (live[u]) {
-                    outt[(g[u] * Pout) * Jout + j[u]] = o;
-                    if (g[u] != gacc) {
-                        part[gacc * 33 + lane] = acc;
-                        acc = 0.f;
-                        gacc = g[u];
+                    float4* orow;
+                    if constexpr (TF) {
+                        if (Pout == 1) orow = outt + q;
+                        else orow = outt + (q + (int)__umulhi((uint32_t)q, jmagic) * out_skip);
+                    } else {
+                        orow = outt + (q + gq_[u] * out_skip);
                     }
-                    acc += o.w;
-                    // further clusters of the same frame are rare with one person per camera: rolled cold path
-                    for (int k = 1; k < Pout; ++k) {
-                        const unsigned mk = multi ? meta[g[u] * Pout + k] : 0u;
-                        outt[(g[u] * Pout + k) * Jout + j[u]] =
-                            mk ? p1_item_exact<T, TD, C>(a, kpt + off[u], sct + off[u], mk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live) *orow = o;
+                    ks[u] = live ? o.w : 0.f;
+                    if (sizeof(T) == 4 && margin[u] < guard_w && live) {
+                        // a float32 distance within the guard band of dthr: decide in float64 and store again (rare)
+                        const int off = q + (int)__umulhi((uint32_t)q, jmagic) * in_skip;
+                        const float4 ex = p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mask[u]);
+                        *orow = ex;
+                        ks[u] = ex.w;
+                    }
+                    if (Pout > 1 && live) {
+                        // further clusters of the same frame are rare with one person per camera: rolled cold path
+                        const int gg = (int)__umulhi((uint32_t)q, jmagic);
+                        const int off = q + gg * in_skip;
+                        for (int k = 1; k < Pout; ++k) {
+                            const unsigned mk = multi ? meta[gg * Pout + k] : 0u;
+                            orow[k * Jout] = mk ? p1_item_exact<T, TD, C>(a, kpt + off, sct + off, mk) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
-            }
+                if (Jout >= STEP) {
+                    // items [Q, Q + STEP) of the tile: does frame gA end inside?  (warp-uniform)
+                    const uint32_t Q = (uint32_t)st * STEP, gA = __umulhi(Q, jmagic);
+                    const int bnd = (int)((gA + 1u) * (uint32_t)Jout - Q);  // items of the step that still belong to frame gA
+                    if (bnd > STEP) {
 #pragma unroll
-            for (int u = 0; u < NI; ++u) {
-                g[u] = gn[u];
-                j[u] = jn[u];
+                        for (int u = 0; u < NI; ++u) acc += ks[u];
+                    } else {
+                        float next = 0.f;
+#pragma unroll
+                        for (int u = 0; u < NI; ++u) {
+                            const bool old = lane + 32 * u < bnd;
+                            acc += old ? ks[u] : 0.f;
+                            next += old ? 0.f : ks[u];
+                        }
+                        const float tot = warp_sum(acc);
+                        if (lane == 0) a.pscores[(size_t)(f0 + (int)gA) * Pout] = tot / (float)Jout;
+                        acc = next;
+                    }
+                }
             }
-        }
-        if (lane < nitems) part[gacc * 33 + lane] = acc;
+        };
+        if (tile_full) run_steps(BoolC<true>{});
+        else run_steps(BoolC<false>{});
         __syncwarp();
 
-        // ---- person score = mean keypoint score (reference :150) ----------------------------------------
-        // lane gg adds up the 32 columns of frame gg (row stride 33: conflict-free), four running sums
-        if (lane < Gc) {
-            const float* row = part + lane * 33;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-                s0 += row[i];
-                s1 += row[i + 1];
-                s2 += row[i + 2];
-                s3 += row[i + 3];
+        // ---- person scores not produced in the loop ------------------------------------------------------
+        // Slot 0 when a step can hold several frame ends (Jout < 32*NI: short skeletons), and the rows of later
+        // clusters when some frame of the tile has one: the keypoint scores were just written by this warp and a
+        // tile of such rows is small, so they are read back from L2.  Fixed summation order.
+        if (Jout < STEP || multi) {
+            for (int row = 0; row < Gc * Pout; ++row) {
+                if (!(row % Pout == 0 ? Jout < STEP : multi)) continue;
+                const float4* o = outt + (size_t)row * Jout;
+                float sum = 0.f;
+                for (int jj = lane; jj < Jout; jj += 32) sum += __ldcg(&o[jj].w);
+                sum = warp_sum(sum);
+                if (lane == 0) a.pscores[(size_t)f0 * Pout + row] = sum / (float)Jout;
             }
-            a.pscores[(size_t)(f0 + lane) * Pout] = ((s0 + s1) + (s2 + s3)) / (float)Jout;
         }
         if (!multi) {
             for (int row = lane; row < Gc * Pout; row += 32)
                 if (row % Pout) a.pscores[(size_t)f0 * Pout + row] = 0.f;
-        } else {  // rows of later clusters, just written by this warp: read back (rare)
-            for (int row = 0; row < Gc * Pout; ++row) {
-                if (row % Pout == 0) continue;
-                const float4* o = reinterpret_cast<const float4*>(a.out) + ((size_t)f0 * Pout + row) * Jout;
-                float s = 0.f;
-                for (int jj = lane; jj < Jout; jj += 32) s += __ldcg(&o[jj].w);
-                s = warp_sum(s);
-                if (lane == 0) a.pscores[(size_t)f0 * Pout + row] = s / (float)Jout;
-            }
         }
         __syncwarp();
     }

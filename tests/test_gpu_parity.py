@@ -829,7 +829,7 @@ def test_jit_failure_falls_back_to_precompiled_kernel(torch_cuda, monkeypatch):
     eng = _engine(rig, synth.DEFAULT_PARAMS, precision="f32")
     eng.set_jit("off")
     base = eng.run(kp, sc, cn, Pout=1)["out"].clone()
-    monkeypatch.setenv("SNOWTRI_JIT_DEFINES", "P1_NI=not_a_number")
+    monkeypatch.setenv("SNOWTRI_JIT_DEFINES", "P1_KEEP=(")
     eng.set_jit("always")
     res = eng.run(kp, sc, cn, Pout=1)
     torch.cuda.synchronize()

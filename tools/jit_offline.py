@@ -39,13 +39,14 @@ for arg in sys.argv[1:]:
         defs["P1_NI"] = "1"
         continue
     defs[k] = v or "1"
+minb = defs.pop("MINB", "2")
 src = "#define P1_JIT 1\n" + "".join(f"#define {k} {v}\n" for k, v in defs.items())
 src += f"#define P1_JIT_J {J}\n#define P1_JIT_JOUT {J}\n#define P1_JIT_POUT {Pout}\n#define P1_JIT_GW {Gw}\n"
 src += f"#define P1_JIT_KST {0.5:.9e}f\n#define P1_JIT_INV_DTHR {inv_dthr:.9e}f\n#define P1_JIT_GUARD_W {inv_dthr * 1e-3:.9e}f\n"
 src += f"#define P1_JIT_KSCALE_FULL {0.0005 / NP:.9e}f\n"
 src += "#define P1_JIT_CAMC {" + ",".join(f"{v:.9e}f" for v in camc) + "}\n"
 src += "#define P1_JIT_PDC {" + ",".join(f"{v:.9e}f" for v in pdc) + "}\n"
-src += ('#include "snowtri_p1.cuh"\nextern "C" __global__ void __launch_bounds__(256, 2) p1_jit('
+src += ('#include "snowtri_p1.cuh"\nextern "C" __global__ void __launch_bounds__(256, ' + minb + ') p1_jit('
         f"const __grid_constant__ snowtri::P1Args<float, 4> a) {{ snowtri::p1_body<float, {TD}, 4, 256>(a); }}\n")
 out = "/tmp/p1_jit_offline"
 open(out + ".cu", "w").write(src)
