@@ -388,12 +388,16 @@ def e2e_block(torch, dist, eng, kpts, scores, out, pout, kp_per_step, steps, wor
             for k in ho_t:
                 ho_t[k].copy_(out[k], non_blocking=True)
     copies()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(esteps):
-        copies()
+    copies()
     torch.cuda.synchronize()
-    dtc = maxed(time.perf_counter() - t0)
+    dtc = float("inf")
+    for _ in range(2):   # best of two passes: the first one still pays for page-table and link warm-up at N > 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            copies()
+        torch.cuda.synchronize()
+        dtc = min(dtc, maxed(time.perf_counter() - t0))
     h2d = int(kpts.numel() * 4 + scores.numel() * 4)
     d2h = int(sum(v.nbytes for v in ho.values()))
     del dk, ds

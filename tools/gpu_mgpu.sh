@@ -5,13 +5,15 @@ mkdir -p $out
 nvidia-smi --query-gpu=index,name --format=csv > $out/gpus.txt 2>&1
 timeout 900 python -m pytest tests/test_multi_gpu.py -m gpu -q -x > $out/pytest_multi_gpu.log 2>&1; echo "pytest rc=$?" >> $out/pytest_multi_gpu.log
 tail -5 $out/pytest_multi_gpu.log
-for n in $(seq 1 $N); do
+for n in ${NLIST:-$(seq 1 $N)}; do
   case $n in 1|2|4|8) ;; *) continue;; esac
+  t0=$SECONDS
   if [ $n -eq 1 ]; then
     timeout 1200 python bench.py --gpus 1 --steps 10 --warmup 3 --no-cpu > $out/bench_${n}gpu.json 2> $out/bench_${n}gpu.err
   else
     timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $n --steps 10 --warmup 3 > $out/bench_${n}gpu.json 2> $out/bench_${n}gpu.err
   fi
+  echo "N=$n bench wall $((SECONDS-t0)) s"
   python - <<PY
 import json
 try:
