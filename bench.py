@@ -333,8 +333,10 @@ def timed_steps(torch, dist, eng, kpts, scores, pout, out, steps, warmup, world,
     if nvtx:
         torch.cuda.nvtx.range_push(nvtx)      # lets `ncu --nvtx --nvtx-include timed/` list exactly these launches
     ev0.record()
+    h0 = time.perf_counter()
     for _ in range(steps):
         eng.run(kpts, scores, None, Pout=pout, out=out)
+    host_ms = (time.perf_counter() - h0) * 1e3   # host time to enqueue the K steps (diagnostic: must stay below the device time)
     ev1.record()
     barrier()
     if nvtx:
@@ -343,6 +345,11 @@ def timed_steps(torch, dist, eng, kpts, scores, pout, out, steps, warmup, world,
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        per = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(per, torch.tensor([ms, host_ms], dtype=torch.float64, device=dev))
+        timed_steps.per_rank = {"device_ms": [round(float(p[0]), 4) for p in per], "host_enqueue_ms": [round(float(p[1]), 4) for p in per]}
+    else:
+        timed_steps.per_rank = {"device_ms": [round(ms, 4)], "host_enqueue_ms": [round(host_ms, 4)]}
     return float(t.item()), ms, eng.launch_count - l0
 
 
@@ -732,6 +739,7 @@ def main():
         time.sleep(0.15)
     ms_max, ms, launches = timed_steps(torch, dist, eng, kpts, scores, pout, out, steps, warmup, world, dev, nvtx="timed")
     launch_info = eng.last_launch_info()
+    per_rank_timing = dict(timed_steps.per_rank)
     if rank == 0:
         time.sleep(0.1)
     clocks = sampler.stop() if rank == 0 else None
@@ -851,7 +859,7 @@ def main():
                 "config": {"workload": wl, "description": desc, "C": C, "P": P, "J": J, "frames_per_gpu": F,
                            "thresholds": prm, "Pout": pout, "timing": "inputs_larger_than_L2" if in_bytes > 126e6 else "inputs_fit_L2",
                            "input_bytes_per_gpu": int(in_bytes), "launch": launch_info},
-                "gpu_launches": int(launches), "jit": jit_status, "clocks": clocks, "parity": parity, "e2e": e2e,
+                "gpu_launches": int(launches), "timed_region_per_rank_ms": {**per_rank_timing, "what": f"the {steps} timed steps: CUDA-event time and host time to enqueue them, per rank"}, "jit": jit_status, "clocks": clocks, "parity": parity, "e2e": e2e,
                 "roofline": roofline, "other_precisions": others, "allgather": gather, "downstream": downstream,
                 "secondary": secondary or None, "host": {"cpus_visible": len(all_cpus), "cpu_count": os.cpu_count()}}
         if value_with_gather is not None:

@@ -47,6 +47,12 @@ struct snowtri_handle {
     size_t p1_args_bytes;
     int jit_mode;             // 0 off, 1 auto (long batches), 2 always
     void* jit_cache;          // rig-specialised kernels (snowtri_jit.cu)
+    // the last rig-specialised launch (snowtri_p1.cu): same argument block and batch shape -> same kernel, no source
+    // string is rebuilt and hashed on the way to the launch
+    unsigned long long p1_fast_key;
+    void* p1_fast_fn;
+    int p1_fast_grid, p1_fast_gw;
+    size_t p1_fast_smem;
     char jit_status[512];
     void* nccl_comm;          // communicator owned by the handle (snowtri_comm.cu), or NULL
     int nccl_nranks, nccl_rank;
