@@ -147,8 +147,7 @@ int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs
  * Batches of up to 256 frames run in one launch with a sequential frame loop (the recurrence is sequential);
  * longer batches are cut into 128-frame chunks that run in parallel, with the state handed from chunk to
  * chunk through powers of the (affine) update matrix: a prefix scan of the chunk maps in one launch --
- * snowtri_smooth_set_chunked(s, 0) forces the sequential kernel, (s, 2) the older three-launch walk over
- * groups of chunks (kept for comparison), (s, 1) is the default.
+ * snowtri_smooth_set_chunked(s, 0) forces the sequential kernel.
  * max_persons bounds n0: create the state with at least as many followers as the FIRST frame of the clip can hold
  * persons (max_persons >= Pout is always enough).  A first frame with more persons than max_persons seeds followers
  * for the first max_persons of them only -- the reference would keep one follower per first-frame person -- and the

@@ -43,7 +43,6 @@ struct snowtri_blender_smooth_state {
     double* d_work;   // chunk-parallel path: per chunk 33 values per (person, control point), see kBsWork
     size_t work_chunks;
     int sequential;   // 1 = always the single-launch sequential kernel
-    int walk_carry;   // 1 = three-launch walk over groups of chunks instead of the scan kernel
 };
 
 namespace snowtri {
@@ -470,14 +469,8 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
     }
 }
 
-// pass B, three short launches over groups of kBsGroup chunks (chunk 0 carries M = 0 and b = its true end state,
-// so the chain start_(c+1) = M_c start_c + b_c holds for every chunk from an arbitrary start_0):
-//   B1  every (group, person, control point) composes the maps of its chunks into one map (Mg, bg);
-//   B2  per (person, control point), sequentially over the groups: start state of every group; the state after the
-//       last group goes back to the persistent state;
-//   B3  every (group, person, control point) walks its chunks again from the group's start state and leaves
-//       start_c for pass C.
-constexpr int kBsGroup = 32;
+// pass B (chunk 0 carries M = 0 and b = its true end state, so the chain start_(c+1) = M_c start_c + b_c holds for
+// every chunk from an arbitrary start_0): see blender_smooth_carry_scan_kernel below.
 
 struct Affine {   // s -> M s + b for the four channels of a control point
     double M[9], b[12];
@@ -498,84 +491,11 @@ __device__ __forceinline__ void affine_apply(const Affine& f, double* s) {   // 
     }
 }
 
-__global__ void __launch_bounds__(96) blender_smooth_carry_compose_kernel(const BsChunkArgs ca, double* gwork, int ngroups) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = gtid / ca.NT, tid = gtid % ca.NT;
-    if (g >= ngroups) return;
-    const int c0 = g * kBsGroup, c1 = min(ca.nchunks, c0 + kBsGroup);
-    Affine acc, cur, nxt;
-    affine_load(acc, ca.work + (size_t)c0 * kBsWork * ca.NT + tid, ca.NT);
-    if (c0 + 1 < c1) affine_load(nxt, ca.work + (size_t)(c0 + 1) * kBsWork * ca.NT + tid, ca.NT);
-    for (int c = c0 + 1; c < c1; ++c) {
-        cur = nxt;
-        if (c + 1 < c1) affine_load(nxt, ca.work + (size_t)(c + 1) * kBsWork * ca.NT + tid, ca.NT);
-        // acc <- cur o acc
-        double M[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int q = 0; q < 3; ++q)
-                M[3 * r + q] = cur.M[3 * r] * acc.M[q] + cur.M[3 * r + 1] * acc.M[3 + q] + cur.M[3 * r + 2] * acc.M[6 + q];
-        affine_apply(cur, acc.b);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) acc.M[i] = M[i];
-    }
-    double* w = gwork + (size_t)g * kBsWork * ca.NT + tid;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) w[(size_t)i * ca.NT] = acc.M[i];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) w[(size_t)(9 + i) * ca.NT] = acc.b[i];
-}
-
-__global__ void __launch_bounds__(96) blender_smooth_carry_groups_kernel(const BsChunkArgs ca, double* gwork, int ngroups) {
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= ca.NT) return;
-    double s[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = 0.0;   // arbitrary: chunk 0 has M = 0
-    Affine cur, nxt;
-    affine_load(nxt, gwork + tid, ca.NT);
-    for (int g = 0; g < ngroups; ++g) {
-        cur = nxt;
-        if (g + 1 < ngroups) affine_load(nxt, gwork + (size_t)(g + 1) * kBsWork * ca.NT + tid, ca.NT);
-        double* w = gwork + (size_t)g * kBsWork * ca.NT + tid;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) w[(size_t)(21 + i) * ca.NT] = s[i];
-        affine_apply(cur, s);
-    }
-    double* st = ca.s.state + 2 + (size_t)tid * 12;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        st[i] = s[3 * i];
-        st[4 + i] = s[3 * i + 1];
-        st[8 + i] = s[3 * i + 2];
-    }
-}
-
-__global__ void __launch_bounds__(96) blender_smooth_carry_chunks_kernel(const BsChunkArgs ca, const double* gwork, int ngroups) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = gtid / ca.NT, tid = gtid % ca.NT;
-    if (g >= ngroups) return;
-    const int c0 = g * kBsGroup, c1 = min(ca.nchunks, c0 + kBsGroup);
-    double s[12];
-#pragma unroll
-    for (int i = 0; i < 12; ++i) s[i] = gwork[((size_t)g * kBsWork + 21 + i) * ca.NT + tid];
-    Affine cur, nxt;
-    affine_load(nxt, ca.work + (size_t)c0 * kBsWork * ca.NT + tid, ca.NT);
-    for (int c = c0; c < c1; ++c) {
-        cur = nxt;
-        if (c + 1 < c1) affine_load(nxt, ca.work + (size_t)(c + 1) * kBsWork * ca.NT + tid, ca.NT);
-        double* w = ca.work + (size_t)c * kBsWork * ca.NT + tid;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) w[(size_t)(21 + i) * ca.NT] = s[i];
-        affine_apply(cur, s);
-    }
-}
-
-// Pass B in ONE launch (default): the hand-over is a prefix scan of the chunk maps under composition.  One CTA per
+// Pass B, one launch: the hand-over is a prefix scan of the chunk maps under composition.  One CTA per
 // (person, control point), a thread per chunk (blocks of kBsScanThreads chunks, the state carried from block to block):
 // Hillis-Steele scan by warp shuffles, the warp totals scanned by warp 0, every thread applies the prefix of the chunks
-// before it.  Replaces 96 dependent memory round trips (26 + 24 + 30 us per 1024 chunks) by two.
+// before it.  (Round 1 walked the chunks in three launches over groups of 32: 96 dependent memory round trips,
+// 26 + 24 + 30 us per 1024 chunks; this kernel takes 36.5 us, profiles/r2p.)
 constexpr int kBsScanThreads = 256;
 __device__ __forceinline__ Affine affine_compose(const Affine& later, const Affine& earlier) {  // later(earlier(s))
     Affine r;
@@ -771,7 +691,6 @@ extern "C" int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s) {
 extern "C" int snowtri_blender_smooth_set_chunked(snowtri_blender_smooth_t* s, int enabled) {
     if (!s) return SNOWTRI_E_ARG;
     s->sequential = enabled ? 0 : 1;
-    s->walk_carry = enabled == 2 ? 1 : 0;
     return SNOWTRI_OK;
 }
 
@@ -819,7 +738,7 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
             if (s->d_work) cudaFree(s->d_work);
             s->d_work = nullptr;
             s->work_chunks = 0;
-            const size_t maps = (size_t)ca.nchunks + (ca.nchunks + kBsGroup - 1) / kBsGroup;   // chunks, then groups
+            const size_t maps = (size_t)ca.nchunks;
             CUDA_TRY(h, cudaMalloc(&s->d_work, maps * kBsWork * threads * sizeof(double)));
             s->work_chunks = (size_t)ca.nchunks;
         }
@@ -827,17 +746,7 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
         const long long ta = (long long)ca.nchunks * threads, tc = (long long)(ca.nchunks - 1) * threads;
         if (f64) blender_smooth_chunk_kernel<double4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
         else blender_smooth_chunk_kernel<float4, 0><<<(unsigned)((ta + 95) / 96), 96, 0, st>>>(ca);
-        if (s->walk_carry) {   // the three-launch walk over groups of chunks (kept for comparison)
-            const int ngroups = (ca.nchunks + kBsGroup - 1) / kBsGroup;
-            double* gwork = s->d_work + (size_t)ca.nchunks * kBsWork * threads;
-            const unsigned gblocks = (unsigned)(((long long)ngroups * threads + 95) / 96);
-            blender_smooth_carry_compose_kernel<<<gblocks, 96, 0, st>>>(ca, gwork, ngroups);
-            blender_smooth_carry_groups_kernel<<<(threads + 95) / 96, 96, 0, st>>>(ca, gwork, ngroups);
-            blender_smooth_carry_chunks_kernel<<<gblocks, 96, 0, st>>>(ca, gwork, ngroups);
-            h->launches += 2;
-        } else {
-            blender_smooth_carry_scan_kernel<<<threads, kBsScanThreads, 0, st>>>(ca);
-        }
+        blender_smooth_carry_scan_kernel<<<threads, kBsScanThreads, 0, st>>>(ca);
         if (f64) blender_smooth_chunk_kernel<double4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
         else blender_smooth_chunk_kernel<float4, 2><<<(unsigned)((tc + 95) / 96), 96, 0, st>>>(ca);
         CUDA_TRY(h, cudaGetLastError());

@@ -109,8 +109,12 @@ extern "C" int snowtri_destroy(snowtri_t* h) {
     free(h->mf_args);
     if (h->pipe_in) {
         cudaStreamDestroy(h->pipe_in);
+        cudaStreamDestroy(h->pipe_k);
         cudaStreamDestroy(h->pipe_out);
-        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i) cudaEventDestroy(h->pipe_ev[i]);
+        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i) {
+            cudaEventDestroy(h->pipe_ev[i]);
+            cudaEventDestroy(h->pipe_evh[i]);
+        }
         cudaEventDestroy(h->pipe_start);
     }
     if (h->d_cam) cudaFree(h->d_cam);
@@ -430,23 +434,30 @@ extern "C" int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* 
         if (rc) return rc;
     }
     cudaStream_t st = (cudaStream_t)stream;
-    // Chunked pipeline over two internal streams: chunk i's device->host copy (stream `out`) overlaps
-    // chunk i+1's host->device copy and kernel (stream `in`), so the PCIe link carries both directions
-    // at once.  Small batches go through in one chunk.
+    // Chunked pipeline over three internal streams: chunk i's kernels (stream `k`) and its device->host copy (stream
+    // `out`) overlap the host->device copy of the chunks behind it (stream `in`), so the PCIe link carries both
+    // directions at once and never waits for a kernel.  Small batches go through in one chunk.
     if (!h->pipe_in) {
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pipe_in, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pipe_k, cudaStreamNonBlocking));
         CUDA_TRY(h, cudaStreamCreateWithFlags(&h->pipe_out, cudaStreamNonBlocking));
-        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i)
+        for (int i = 0; i < SNOWTRI_PIPE_EVENTS; ++i) {
             CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming));
+            CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_evh[i], cudaEventDisableTiming));
+        }
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->pipe_start, cudaEventDisableTiming));
     }
     const size_t in_per_frame = (size_t)h->C * P * J * 12;
     int chunk = h->tune_chunk > 0 ? h->tune_chunk : (int)((size_t)(24u << 20) / in_per_frame);  // ~24 MB of input per chunk
+    // several persons per camera: the matching kernel runs one CTA per frame, two per SM -- a chunk should be a few full
+    // waves of them (at 24 MB, BASELINE configs[2] had 492-frame chunks = 1.7 waves)
+    if (h->tune_chunk <= 0 && P > 1 && chunk < 8 * h->sm_count) chunk = 8 * h->sm_count;
     if (chunk < 1) chunk = 1;
     if (chunk > F) chunk = F;
     const int nchunks = (F + chunk - 1) / chunk;
     CUDA_TRY(h, cudaEventRecord(h->pipe_start, st));            // order the pipeline after the caller's stream
     CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_in, h->pipe_start, 0));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_k, h->pipe_start, 0));
     CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_out, h->pipe_start, 0));
     const size_t rpf = (size_t)h->C * P * J, opf = (size_t)Pout * keypoint_num;
     for (int ci = 0; ci < nchunks; ++ci) {
@@ -461,16 +472,20 @@ extern "C" int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* 
         CUDA_TRY(h, cudaMemcpyAsync(ds, h_scores + (size_t)f0 * rpf, (size_t)fc * rpf * 4, cudaMemcpyHostToDevice, h->pipe_in));
         if (h_counts)
             CUDA_TRY(h, cudaMemcpyAsync(dc, h_counts + (size_t)f0 * h->C, (size_t)fc * h->C * 4, cudaMemcpyHostToDevice, h->pipe_in));
-        const int rc = snowtri_run(h, dk, ds, h_counts ? dc : nullptr, fc, P, J, keypoint_num, Pout, dout, dps, dn, h->pipe_in);
+        cudaEvent_t evh = h->pipe_evh[ci % SNOWTRI_PIPE_EVENTS];
+        CUDA_TRY(h, cudaEventRecord(evh, h->pipe_in));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_k, evh, 0));
+        const int rc = snowtri_run(h, dk, ds, h_counts ? dc : nullptr, fc, P, J, keypoint_num, Pout, dout, dps, dn, h->pipe_k);
         if (rc) return rc;
         cudaEvent_t ev = h->pipe_ev[ci % SNOWTRI_PIPE_EVENTS];
-        CUDA_TRY(h, cudaEventRecord(ev, h->pipe_in));
+        CUDA_TRY(h, cudaEventRecord(ev, h->pipe_k));
         CUDA_TRY(h, cudaStreamWaitEvent(h->pipe_out, ev, 0));
         CUDA_TRY(h, cudaMemcpyAsync(h_out + (size_t)f0 * opf * 4, dout, (size_t)fc * opf * 16, cudaMemcpyDeviceToHost, h->pipe_out));
         CUDA_TRY(h, cudaMemcpyAsync(h_pscores + (size_t)f0 * Pout, dps, (size_t)fc * Pout * 4, cudaMemcpyDeviceToHost, h->pipe_out));
         CUDA_TRY(h, cudaMemcpyAsync(h_nout + f0, dn, (size_t)fc * 4, cudaMemcpyDeviceToHost, h->pipe_out));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->pipe_out));
+    CUDA_TRY(h, cudaStreamSynchronize(h->pipe_k));
     CUDA_TRY(h, cudaStreamSynchronize(h->pipe_in));
     return SNOWTRI_OK;
 }

@@ -34,8 +34,8 @@ struct snowtri_handle {
     // device staging owned by the handle (snowtri_run_host only)
     void* stage[6];
     // two-stream pipeline of snowtri_run_host
-    cudaStream_t pipe_in, pipe_out;
-    cudaEvent_t pipe_ev[SNOWTRI_PIPE_EVENTS], pipe_start;
+    cudaStream_t pipe_in, pipe_k, pipe_out;   // host->device copies, kernels, device->host copies of snowtri_run_host
+    cudaEvent_t pipe_ev[SNOWTRI_PIPE_EVENTS], pipe_evh[SNOWTRI_PIPE_EVENTS], pipe_start;
     int tune_chunk;  // frames per pipeline chunk (0 = automatic)
     void* gen_scratch;        // candidate scratch of the streaming general path
     size_t gen_scratch_bytes;

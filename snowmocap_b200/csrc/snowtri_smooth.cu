@@ -15,8 +15,8 @@
 // affine in the state (xp, y, yd): s' = A s + b x):
 //   pass A  every (chunk, person, joint) runs the recurrence over its chunk from a ZERO state -> b_c, and
 //           counts the frames n_c in which its person was present;
-//   pass B  per (person, joint), sequentially over the chunks: start_c+1 = A^n_c start_c + b_c (A^n from a
-//           table computed on the host);
+//   pass B  start_c+1 = A^n_c start_c + b_c (A^n from a table computed on the host) for every chunk: a prefix scan
+//           of the chunk maps under composition, one launch (smooth_carry_scan_kernel);
 //   pass C  every (chunk, person, joint) runs the recurrence again from its true start state and writes the
 //           smoothed points.
 // Inside a chunk the arithmetic is the reference's sequential recurrence; only the hand-over between chunks
@@ -37,12 +37,10 @@ struct snowtri_smooth_state {
     // chunk-parallel path
     double* d_work;   // per chunk: b (P,J,9) then start (P,J,9)
     int* d_cnt;       // per chunk: present-frame count per person (P), then a "seeded here" flag
-    double* d_gmap;   // per group of chunks: composed affine map (12) and start state (3) per (person, joint, axis)
     double* d_apow;   // (kChunk+1, 9) powers of the state matrix for the current delta_time
     size_t work_chunks;
     double apow_T;
     int sequential;   // 1 = always the single-launch sequential kernel
-    int walk_carry;   // 1 = hand the state over with the three-launch walk instead of the scan kernel
     double apow_host[(128 + 1) * 9];  // (kChunk + 1) matrices
 };
 
@@ -256,137 +254,13 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
     }
 }
 
-// Pass B: hand the state from chunk to chunk.  A plain walk over the chunks is one memory latency per chunk
-// (1024 chunks = 0.56 ms for a 131 072-frame batch), so the walk has two levels over groups of kGroup chunks:
-//   B1  per (group, person, joint, axis): compose the group's affine maps  s -> M s + o   (parallel over groups)
-//   B2  per (person, joint, axis): walk the groups with the composed maps; store the clip state for the next call
-//   B3  per (group, person, joint, axis): walk the group's chunks from the group's start state -> chunk starts
-// A chunk whose first frame seeded the followers is the constant map s -> b.
-constexpr int kGroup = 32;
-
-struct CarryCtx {
-    const double* apow;
-    int chn, c, k, n0;
-    size_t nch;
-};
-
-__device__ __forceinline__ bool carry_setup(const ChunkArgs& ca, double* apow_s, CarryCtx& x, int tid) {
-    const SmoothArgs& a = ca.s;
-    for (int i = threadIdx.x; i < (kChunk + 1) * 9; i += blockDim.x) apow_s[i] = ca.apow[i];
-    __syncthreads();
-    x.apow = apow_s;
-    x.chn = tid / 3;
-    x.c = tid - x.chn * 3;
-    x.k = x.chn / a.J;
-    x.nch = (size_t)a.P * a.J;
-    const bool was_init = a.state[0] != 0.0;
-    x.n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
-    return tid < a.P * a.J * 3;
-}
-
-// B1: composite map of one group of chunks.  gmap: (ngroups, P*J*3, 12) = M row-major (9), o (3).
-__global__ void __launch_bounds__(128) smooth_carry_compose_kernel(const ChunkArgs ca, double* gmap, int ngroups) {
-    __shared__ double apow_s[(kChunk + 1) * 9];
-    const SmoothArgs& a = ca.s;
-    const int nthr = a.P * a.J * 3;
-    const int g = blockIdx.y, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    CarryCtx x;
-    if (!carry_setup(ca, apow_s, x, tid)) return;
-    double M[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, o[3] = {0, 0, 0};
-    const int c_end = min(ca.nchunks, (g + 1) * kGroup);
-    for (int chunk = g * kGroup; chunk < c_end; ++chunk) {
-        const double* wb = ca.work + (size_t)chunk * x.nch * 18 + (size_t)x.chn * 9 + x.c;
-        const double b0 = wb[0], b1 = wb[3], b2 = wb[6];
-        const int n = ca.cnt[(size_t)chunk * (a.P + 1) + x.k];
-        const bool seeded = ca.cnt[(size_t)chunk * (a.P + 1) + a.P] != 0 && x.k < x.n0;
-        if (seeded) {
-#pragma unroll
-            for (int i = 0; i < 9; ++i) M[i] = 0.0;
-            o[0] = b0; o[1] = b1; o[2] = b2;
-        } else {
-            const double* A = x.apow + n * 9;
-            double Mn[9];
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int q = 0; q < 3; ++q) Mn[r * 3 + q] = A[r * 3] * M[q] + A[r * 3 + 1] * M[3 + q] + A[r * 3 + 2] * M[6 + q];
-            const double o0 = b0 + A[0] * o[0] + A[1] * o[1] + A[2] * o[2];
-            const double o1 = b1 + A[3] * o[0] + A[4] * o[1] + A[5] * o[2];
-            const double o2 = b2 + A[6] * o[0] + A[7] * o[1] + A[8] * o[2];
-#pragma unroll
-            for (int i = 0; i < 9; ++i) M[i] = Mn[i];
-            o[0] = o0; o[1] = o1; o[2] = o2;
-        }
-    }
-    double* gm = gmap + ((size_t)g * nthr + tid) * 12;
-#pragma unroll
-    for (int i = 0; i < 9; ++i) gm[i] = M[i];
-    gm[9] = o[0]; gm[10] = o[1]; gm[11] = o[2];
-}
-
-// B2: walk the groups; gstart: (ngroups, P*J*3, 3) start state of every group.
-__global__ void __launch_bounds__(128) smooth_carry_groups_kernel(const ChunkArgs ca, const double* gmap, double* gstart,
-                                                                  int ngroups) {
-    const SmoothArgs& a = ca.s;
-    const int nthr = a.P * a.J * 3;
-    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= nthr) return;
-    const int chn = tid / 3, c = tid - chn * 3;
-    const size_t N = (size_t)a.P * a.J * 3;
-    double* sxp = a.state + 2 + (size_t)chn * 3 + c;
-    double* sy = sxp + N;
-    double* syd = sy + N;
-    double v0 = *sxp, v1 = *sy, v2 = *syd;
-    for (int g = 0; g < ngroups; ++g) {
-        double* gs = gstart + ((size_t)g * nthr + tid) * 3;
-        gs[0] = v0; gs[1] = v1; gs[2] = v2;
-        const double* gm = gmap + ((size_t)g * nthr + tid) * 12;
-        const double t0 = gm[9] + gm[0] * v0 + gm[1] * v1 + gm[2] * v2;
-        const double t1 = gm[10] + gm[3] * v0 + gm[4] * v1 + gm[5] * v2;
-        const double t2 = gm[11] + gm[6] * v0 + gm[7] * v1 + gm[8] * v2;
-        v0 = t0; v1 = t1; v2 = t2;
-    }
-    *sxp = v0;
-    *sy = v1;
-    *syd = v2;
-}
-
-// B3: start state of every chunk of a group.
-__global__ void __launch_bounds__(128) smooth_carry_chunks_kernel(const ChunkArgs ca, const double* gstart, int ngroups) {
-    __shared__ double apow_s[(kChunk + 1) * 9];
-    const SmoothArgs& a = ca.s;
-    const int nthr = a.P * a.J * 3;
-    const int g = blockIdx.y, tid = blockIdx.x * blockDim.x + threadIdx.x;
-    CarryCtx x;
-    if (!carry_setup(ca, apow_s, x, tid)) return;
-    const double* gs = gstart + ((size_t)g * nthr + tid) * 3;
-    double v0 = gs[0], v1 = gs[1], v2 = gs[2];
-    const int c_end = min(ca.nchunks, (g + 1) * kGroup);
-    for (int chunk = g * kGroup; chunk < c_end; ++chunk) {
-        double* wb = ca.work + (size_t)chunk * x.nch * 18 + (size_t)x.chn * 9 + x.c;
-        double* ws = wb + x.nch * 9;
-        ws[0] = v0; ws[3] = v1; ws[6] = v2;
-        const double b0 = wb[0], b1 = wb[3], b2 = wb[6];
-        const int n = ca.cnt[(size_t)chunk * (a.P + 1) + x.k];
-        const bool seeded = ca.cnt[(size_t)chunk * (a.P + 1) + a.P] != 0 && x.k < x.n0;
-        if (seeded) {
-            v0 = b0; v1 = b1; v2 = b2;
-        } else {
-            const double* A = x.apow + n * 9;
-            const double t0 = b0 + A[0] * v0 + A[1] * v1 + A[2] * v2;
-            const double t1 = b1 + A[3] * v0 + A[4] * v1 + A[5] * v2;
-            const double t2 = b2 + A[6] * v0 + A[7] * v1 + A[8] * v2;
-            v0 = t0; v1 = t1; v2 = t2;
-        }
-    }
-}
-
-// Pass B in ONE launch: the chunk maps of a (person, joint, axis) channel are affine, so their hand-over is a prefix
+// Pass B, one launch: the chunk maps of a (person, joint, axis) channel are affine, so their hand-over is a prefix
 // scan under composition.  One CTA per channel, a thread per chunk (blocks of kScanThreads chunks, the state carried
 // from block to block): warp-level Hillis-Steele scan by shuffles (5 levels), the 16 warp totals scanned by warp 0,
 // every thread then applies the prefix of the chunks before it to the clip state.  Two memory round trips and ~10
-// compositions deep instead of the 96 dependent round trips of the three walks above (24.8 + 26.1 + 26.8 us per
-// 1024 chunks, profiles/r2n).  Composition order differs from the sequential walk by rounding only (~1e-15).
+// compositions deep.  (Round 1 walked the chunks in three launches over groups of 32 -- compose the group maps, walk
+// the groups, expand to chunk starts: 96 dependent round trips, 24.8 + 26.1 + 26.8 us per 1024 chunks, profiles/r2n;
+// this kernel takes 39 us, profiles/r2p.)  Composition order differs from a sequential walk by rounding only (~1e-15).
 constexpr int kScanThreads = 512;
 struct AMap {  // s -> M s + o on (xp, y, yd)
     double M[9], o[3];
@@ -557,7 +431,6 @@ extern "C" int snowtri_smooth_destroy(snowtri_smooth_t* s) {
     if (s->d_state) cudaFree(s->d_state);
     if (s->d_work) cudaFree(s->d_work);
     if (s->d_cnt) cudaFree(s->d_cnt);
-    if (s->d_gmap) cudaFree(s->d_gmap);
     if (s->d_apow) cudaFree(s->d_apow);
     free(s);
     return SNOWTRI_OK;
@@ -566,7 +439,6 @@ extern "C" int snowtri_smooth_destroy(snowtri_smooth_t* s) {
 extern "C" int snowtri_smooth_set_chunked(snowtri_smooth_t* s, int enabled) {
     if (!s) return SNOWTRI_E_ARG;
     s->sequential = enabled ? 0 : 1;
-    s->walk_carry = enabled == 2 ? 1 : 0;
     return SNOWTRI_OK;
 }
 
@@ -612,9 +484,7 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
     if (s->work_chunks < (size_t)nchunks) {
         if (s->d_work) cudaFree(s->d_work);
         if (s->d_cnt) cudaFree(s->d_cnt);
-        if (s->d_gmap) cudaFree(s->d_gmap);
-        s->d_work = nullptr; s->d_cnt = nullptr; s->d_gmap = nullptr; s->work_chunks = 0;
-        CUDA_TRY(h, cudaMalloc(&s->d_gmap, (size_t)((nchunks + kGroup - 1) / kGroup) * nch * 3 * 15 * sizeof(double)));
+            s->d_work = nullptr; s->d_cnt = nullptr; s->work_chunks = 0;
         CUDA_TRY(h, cudaMalloc(&s->d_work, (size_t)nchunks * nch * 18 * sizeof(double)));
         CUDA_TRY(h, cudaMalloc(&s->d_cnt, (size_t)nchunks * (s->P + 1) * sizeof(int)));
         s->work_chunks = (size_t)nchunks;
@@ -643,18 +513,7 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
     const unsigned g2 = (unsigned)(((long long)nchunks * threads + 127) / 128);
     if (f64) smooth_chunk_kernel<double4, 0><<<g2, 128, 0, st>>>(ca);
     else smooth_chunk_kernel<float4, 0><<<g2, 128, 0, st>>>(ca);
-    if (s->walk_carry) {   // the three-launch walk over groups of chunks (kept for comparison: snowtri_smooth_set_chunked(s, 2))
-        const int ngroups = (nchunks + kGroup - 1) / kGroup;
-        double* gmap = s->d_gmap;
-        double* gstart = gmap + (size_t)ngroups * nch * 3 * 12;
-        const dim3 gB((threads * 3 + 127) / 128, ngroups);
-        smooth_carry_compose_kernel<<<gB, 128, 0, st>>>(ca, gmap, ngroups);
-        smooth_carry_groups_kernel<<<gB.x, 128, 0, st>>>(ca, gmap, gstart, ngroups);
-        smooth_carry_chunks_kernel<<<gB, 128, 0, st>>>(ca, gstart, ngroups);
-        h->launches += 2;
-    } else {
-        smooth_carry_scan_kernel<<<threads * 3, kScanThreads, 0, st>>>(ca);
-    }
+    smooth_carry_scan_kernel<<<threads * 3, kScanThreads, 0, st>>>(ca);
     if (f64) smooth_chunk_kernel<double4, 2><<<g2, 128, 0, st>>>(ca);
     else smooth_chunk_kernel<float4, 2><<<g2, 128, 0, st>>>(ca);
     smooth_finish_kernel<<<1, 1, 0, st>>>(s->d_state, d_nout, Pout, s->P);
