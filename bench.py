@@ -215,6 +215,16 @@ def cpu_baseline_block(rig, C, P, J, prm, pout, budget_s=10.0):
     return block
 
 
+def workload_config(wl, F):
+    """The `config` object of the JSON line: the workload and nothing about how an arm ran it, so both arms print the
+    same object (the reference arm times a bounded sample of it, described in its `cpu_baseline.sample`)."""
+    _, C, P, J, _, pk, pout, desc = WORKLOADS[wl]
+    in_bytes = F * C * P * J * 12
+    return {"workload": wl, "description": desc, "C": C, "P": P, "J": J, "frames_per_gpu": int(F), "thresholds": params_of(pk),
+            "Pout": pout, "timing": "inputs_larger_than_L2" if in_bytes > 126e6 else "inputs_fit_L2",
+            "input_bytes_per_gpu": int(in_bytes)}
+
+
 def run_reference_arm(args, wl):
     rig_kind, C, P, J, _, pk, pout, desc = WORKLOADS[wl]
     rank = int(os.environ.get("RANK", "0"))
@@ -236,7 +246,7 @@ def run_reference_arm(args, wl):
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": 1e3 * sum(dt for _, dt in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl, "description": desc, "C": C, "P": P, "J": J},
+            "config": workload_config(wl, args.frames if args.frames > 0 else WORKLOADS[wl][4]),
             "cpu_baseline": {"value": value, "unit": "keypoints/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "keypoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
@@ -856,9 +866,7 @@ def main():
         line = {"metric": "3d_keypoints_per_sec", "value": value, "unit": "keypoints/s", "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_max / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": wl, "description": desc, "C": C, "P": P, "J": J, "frames_per_gpu": F,
-                           "thresholds": prm, "Pout": pout, "timing": "inputs_larger_than_L2" if in_bytes > 126e6 else "inputs_fit_L2",
-                           "input_bytes_per_gpu": int(in_bytes), "launch": launch_info},
+                "config": workload_config(wl, F), "launch": launch_info,
                 "gpu_launches": int(launches), "timed_region_per_rank_ms": {**per_rank_timing, "what": f"the {steps} timed steps: CUDA-event time and host time to enqueue them, per rank"}, "jit": jit_status, "clocks": clocks, "parity": parity, "e2e": e2e,
                 "roofline": roofline, "other_precisions": others, "allgather": gather, "downstream": downstream,
                 "secondary": secondary or None, "host": {"cpus_visible": len(all_cpus), "cpu_count": os.cpu_count()}}

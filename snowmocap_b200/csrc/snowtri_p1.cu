@@ -256,7 +256,7 @@ static int run_p1(snowtri_t* h, const float* d_kpts, const float* d_scores, cons
 bool snowtri_p1_eligible(const snowtri_t* h, int P, int Pout, int keypoint_num) {
     const bool all_kept = h->prm.ast <= 0.0 && h->prm.kst >= 0.0;
     const bool never_filter = h->prm.score_tol <= 0.0 && h->prm.kst >= 0.0;
-    return !h->no_p1 && P == 1 && h->C >= 2 && h->C <= 8 && all_kept && never_filter && Pout <= 64 && keypoint_num <= kP1MaxJout;
+    return !h->no_p1 && P == 1 && h->C >= 2 && h->C <= 8 && all_kept && never_filter && Pout <= 64 && keypoint_num >= 2 && keypoint_num <= kP1MaxJout;   // (ceil(2^32 / 1) does not fit the magic constant)
 }
 
 int snowtri_p1_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const int* d_counts, int F, int J,

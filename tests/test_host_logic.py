@@ -247,3 +247,22 @@ def test_bind_host_to_gpu_is_a_noop_without_a_device():
     before = os.sched_getaffinity(0)
     assert bind_host_to_gpu(0) == 0
     assert os.sched_getaffinity(0) == before
+
+
+def test_magic_division_of_the_single_person_kernel_is_exact():
+    """snowtri_p1.cuh walks a tile by the flat item index q and gets the item's frame as umulhi(q, ceil(2^32 / Jout)).
+    The header claims exactness for q < 32 * Jout + 64 as long as Jout <= kP1MaxJout = 8192 (32 * Jout^2 < 2^32): check
+    the claim at the frame boundaries, where an off-by-one would show, for every Jout the kernel accepts."""
+    for d in list(range(2, 300)) + [511, 512, 513, 1000, 4095, 4096, 8191, 8192]:   # one keypoint takes the general path
+        m = ((1 << 32) + d - 1) // d
+        assert m < (1 << 32)
+        qmax = 32 * d + 64
+        qs = set()
+        for g in range(0, 34):
+            for off in (-2, -1, 0, 1):
+                q = g * d + off
+                if 0 <= q <= qmax:
+                    qs.add(q)
+        qs.update((0, 1, qmax - 1, qmax))
+        for q in qs:
+            assert (q * m) >> 32 == q // d, (d, q)

@@ -12,7 +12,7 @@ for so in snowmocap_b200/variants/*.so; do
 import json
 try:
     d=json.load(open("$out/bench_${name}_$prec.json"))
-    print("$name $prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], "relL2=%.2e"%d["parity"]["rel_l2_points"], d["config"]["launch"])
+    print("$name $prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], "relL2=%.2e"%d["parity"]["rel_l2_points"], d["launch"])
 except Exception as e:
     print("$name $prec bench failed", e); print(open("$out/bench_${name}_$prec.err").read()[-1500:])
 PY

@@ -9,7 +9,7 @@ for prec in ${2:-f64 f32x}; do
 import json
 try:
     d=json.load(open("$out/bench_cfg3_$prec.json"))
-    print("$prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["config"]["launch"])
+    print("$prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["launch"])
 except Exception as e:
     print("$prec bench failed", e); print(open("$out/bench_cfg3_$prec.err").read()[-2000:])
 PY

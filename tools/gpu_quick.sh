@@ -11,7 +11,7 @@ for prec in $precs; do
 import json
 try:
     d=json.load(open("$out/bench_cfg2_$prec.json"))
-    print("$prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], d["parity"], d["config"]["launch"], "e2e=", d.get("e2e") and "%.3e"%d["e2e"]["value"])
+    print("$prec", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], d["parity"], d["launch"], "e2e=", d.get("e2e") and "%.3e"%d["e2e"]["value"])
 except Exception as e:
     print("$prec bench failed", e); print(open("$out/bench_cfg2_$prec.err").read()[-2000:])
 PY

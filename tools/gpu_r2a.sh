@@ -17,7 +17,7 @@ for wl in cfg3 cfg4 cfg5; do
 import json
 try:
     d=json.load(open("$out/bench_${wl}_gen$gen.json"))
-    print("$wl gen$gen", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["config"]["launch"]["kernel"], "launches", d["gpu_launches"])
+    print("$wl gen$gen", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["launch"]["kernel"], "launches", d["gpu_launches"])
 except Exception as e:
     print("$wl gen$gen bench failed", e); print(open("$out/bench_${wl}_gen$gen.err").read()[-1500:])
 PY

@@ -11,7 +11,7 @@ for rolled in 0; do
 import json
 try:
     d=json.load(open("$out/bench_cfg3_rolled$rolled.json"))
-    print("cfg3 rolled=$rolled", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["config"]["launch"]["kernel"], "launches", d["gpu_launches"])
+    print("cfg3 rolled=$rolled", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["launch"]["kernel"], "launches", d["gpu_launches"])
 except Exception as e:
     print("cfg3 bench failed", e); print(open("$out/bench_cfg3_rolled$rolled.err").read()[-1500:])
 PY
@@ -25,7 +25,7 @@ for wl in cfg4 cfg5; do
 import json
 try:
     d=json.load(open("$out/bench_${wl}.json"))
-    print("$wl", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["config"]["launch"]["kernel"], "launches", d["gpu_launches"])
+    print("$wl", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["parity"], d["launch"]["kernel"], "launches", d["gpu_launches"])
 except Exception as e:
     print("$wl bench failed", e); print(open("$out/bench_${wl}.err").read()[-1500:])
 PY

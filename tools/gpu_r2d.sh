@@ -9,7 +9,7 @@ python - <<PY
 import json
 try:
     d=json.load(open("$out/bench_cfg3.json"))
-    print("cfg3", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["config"]["launch"]["kernel"], "launches", d["gpu_launches"], d["roofline"]["frac"], d["parity"]["nout_equal"], d["parity"]["rel_l2_points"])
+    print("cfg3", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], d["launch"]["kernel"], "launches", d["gpu_launches"], d["roofline"]["frac"], d["parity"]["nout_equal"], d["parity"]["rel_l2_points"])
 except Exception as e:
     print("cfg3 bench failed", e); print(open("$out/bench_cfg3.err").read()[-1500:])
 PY

@@ -12,7 +12,7 @@ import json
 try:
     d=json.load(open("$out/bench_cfg2_$name.json"))
     p=d["parity"]
-    print("$name", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], d["config"]["launch"], d["jit"][:40], "relL2=%.2e"%p["rel_l2_points"], "ks max=%.1e"%(p["max_rel_err_kscores"]))
+    print("$name", "value=%.3e"%d["value"], "ms=%.4f"%d["ms_per_step"], "frac=%.3f"%d["roofline"]["frac"], d["launch"], d["jit"][:40], "relL2=%.2e"%p["rel_l2_points"], "ks max=%.1e"%(p["max_rel_err_kscores"]))
 except Exception as e:
     print("$name failed", e); print(open("$out/bench_cfg2_$name.err").read()[-800:])
 PY
