@@ -131,7 +131,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     const bool fuse2 = gen2 && C >= 2 && C <= 8 && Pout <= 32 && P <= 255;
     const size_t R = (size_t)C * P * J;
     const size_t mtab = MatchTables::bytes(C, a.npairs);
-    const size_t mstaged = mtab + R * 20;                     // rays (16 B) + scores (4 B) of one frame
+    const size_t mstaged = mtab + match_desc_bytes(a.npairs * ((P + kTile - 1) / kTile) * ((P + kTile - 1) / kTile)) + match_camf_bytes(C) + R * 20;   // item descriptors, rays (16 B) + scores (4 B) of one frame
     const bool match_smem = match2 && !h->no_fly && mstaged <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024;  // two CTAs per SM
     const bool match_glob = match2 && !match_smem;
 

@@ -74,24 +74,47 @@ struct MatchItem {
     const float *qm, *qs;                // their scores
 };
 
-__device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const double* camD, const uchar2* pairs,
-                                                   const float4* rays, const float* scs, int f, int it) {
+// What an item is, independent of the frame: built once per CTA (MatchTables) instead of per (frame, item) -- the index
+// divisions and the float64 centre differences were 6 % of the kernel's instructions (profiles/r2o).
+struct MatchItemDesc {
+    float dx, dy, dz;            // ts - tm
+    unsigned short pair;
+    unsigned char mc, sc, pm0, ps0;
+    unsigned char pad[2];
+};
+__host__ __device__ inline size_t match_camf_bytes(int C) { return ((size_t)C * 36 + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t match_desc_bytes(int items) { return ((size_t)items * sizeof(MatchItemDesc) + 15) & ~(size_t)15; }
+__device__ __forceinline__ MatchItemDesc match_item_desc(const GenArgs& a, const double* camD, const uchar2* pairs, int it) {
+    const int tpp = (a.P + kTile - 1) / kTile;
+    MatchItemDesc q;
+    const int pair = it / (tpp * tpp), tt = it - pair * tpp * tpp;
+    q.pair = (unsigned short)pair;
+    q.pm0 = (unsigned char)((tt / tpp) * kTile);
+    q.ps0 = (unsigned char)((tt % tpp) * kTile);
+    q.mc = pairs[pair].x;
+    q.sc = pairs[pair].y;
+    q.dx = (float)(camD[12 * q.sc + 9] - camD[12 * q.mc + 9]);
+    q.dy = (float)(camD[12 * q.sc + 10] - camD[12 * q.mc + 10]);
+    q.dz = (float)(camD[12 * q.sc + 11] - camD[12 * q.mc + 11]);
+    q.pad[0] = q.pad[1] = 0;
+    return q;
+}
+
+__device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const MatchItemDesc& q, const float4* rays, const float* scs, int f) {
     const int C = a.C, P = a.P, J = a.J;
-    const int tpp = (P + kTile - 1) / kTile;
     MatchItem t;
-    t.pair = it / (tpp * tpp);
-    const int tt = it - t.pair * tpp * tpp;
-    t.pm0 = (tt / tpp) * kTile;
-    t.ps0 = (tt % tpp) * kTile;
-    t.mc = pairs[t.pair].x;
-    t.sc = pairs[t.pair].y;
+    t.pair = q.pair;
+    t.pm0 = q.pm0;
+    t.ps0 = q.ps0;
+    t.mc = q.mc;
+    t.sc = q.sc;
     const int cm = a.counts ? max(0, min(P, a.counts[(size_t)f * C + t.mc])) : P;
     const int cs = a.counts ? max(0, min(P, a.counts[(size_t)f * C + t.sc])) : P;
     t.nm = max(0, min(kTile, cm - t.pm0));
     t.ns = max(0, min(kTile, cs - t.ps0));
-    t.d.x = (float)(camD[12 * t.sc + 9] - camD[12 * t.mc + 9]);
-    t.d.y = (float)(camD[12 * t.sc + 10] - camD[12 * t.mc + 10]);
-    t.d.z = (float)(camD[12 * t.sc + 11] - camD[12 * t.mc + 11]);
+    t.d.x = q.dx;
+    t.d.y = q.dy;
+    t.d.z = q.dz;
     t.rm = rays + (size_t)(t.mc * P + t.pm0) * J;
     t.rs = rays + (size_t)(t.sc * P + t.ps0) * J;
     t.qm = scs + (size_t)(t.mc * P + t.pm0) * J;
@@ -219,9 +242,11 @@ __device__ __forceinline__ void match_decide(const GenArgs& a, const double* cam
 // dropped: the leftover joints of four items sharing one pass -- 11 % fewer instructions, but either the unrolled form
 // outgrows the instruction cache (1.33 -> 1.47 ms at BASELINE configs[2]) or the rolled form pays the saving back in
 // index arithmetic and needs more than the 128 registers two 7-warp CTAs per SM leave (2.03 ms); profiles/r2d, r2e.
-__device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const uchar2* pairs, const float4* rays,
-                                               const float* scs, const float2* kf, const float* sf, int f, int it, int lane) {
-    const MatchItem t = match_item_of(a, camD, pairs, rays, scs, f, it);
+// Also dropped: the leftover joints split over the lanes (32 / tail lanes per joint, 3 evaluations per lane): 4.8 %
+// fewer instructions, but the short dependent tail issues at 70.6 % instead of 74.8 % -- 1.089 vs 1.079 ms, profiles/r2t.
+__device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const MatchItemDesc& q, const float4* rays,
+                                               const float* scs, const float2* kf, const float* sf, int f, int lane) {
+    const MatchItem t = match_item_of(a, q, rays, scs, f);
     const bool sums = !a.all_kept && t.nm > 0 && t.ns > 0;
     float lo_tot = 0.f, hi_tot = 0.f;
     if (sums) {
@@ -267,29 +292,48 @@ __global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
     const int f = blockIdx.x, C = a.C, P = a.P, J = a.J;
     const int R = C * P * J;
-    float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs));
+    const int tpp = (P + kTile - 1) / kTile;
+    const int items = a.npairs * tpp * tpp;
+    MatchItemDesc* idesc = reinterpret_cast<MatchItemDesc*>(smem + MatchTables::bytes(C, a.npairs));
+    float* camF = reinterpret_cast<float*>(smem + MatchTables::bytes(C, a.npairs) + match_desc_bytes(items));  // M of every camera, float32
+    float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs) + match_desc_bytes(items) + match_camf_bytes(C));
     float* scs = reinterpret_cast<float*>(rays + R);
     const float2* kf = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R;
     const float* sf = a.scores + (size_t)f * R;
-    for (int row = warp; row < C * P; row += NW) {  // one (camera, person) row per warp
-        float M[9];
-        const int c = row / P;
+    for (int i = threadIdx.x; i < C * 9; i += blockDim.x) camF[i] = (float)a.cam[(i / 9) * 12 + (i % 9)];
+    __syncthreads();  // the tables
+    for (int it = threadIdx.x; it < items; it += blockDim.x) idesc[it] = match_item_desc(a, tb.camD, tb.pairs, it);
+    // Ray build, a thread per ray: the loads of a batch of rays are issued back to back before any of them is used --
+    // a warp per (camera, person) row with a load-use-store loop over the joints was ~20 dependent memory round trips per
+    // warp and frame, during which the CTA did nothing else (15 % of the stall samples on 2 % of the instructions,
+    // profiles/r2r).
+    {
+        constexpr int NB = 8;
+        const uint32_t pj_magic = (uint32_t)((0x100000000ull + (uint32_t)(P * J) - 1u) / (uint32_t)(P * J));  // exact: C (P J)^2 < 2^32 here
+        for (int i0 = threadIdx.x; i0 < R; i0 += NB * blockDim.x) {
+            float2 q[NB];
+            float sv[NB];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) M[i] = (float)a.cam[12 * c + i];
-        for (int j = lane; j < J; j += 32) {
-            const int i = row * J + j;
-            const float2 q = __ldg(kf + i);
-            const float s = __ldg(sf + i);
-            const V3<float> h = back_project<float>(M, q.x, q.y);
-            const float cc = dot3(h, h);
-            rays[i] = make_float4(h.x, h.y, h.z, s < a.prm.kst_f ? -cc : cc);
-            scs[i] = s;
+            for (int u = 0; u < NB; ++u) {
+                const int i = min(i0 + u * (int)blockDim.x, R - 1);
+                q[u] = __ldg(kf + i);
+                sv[u] = __ldg(sf + i);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int i = i0 + u * (int)blockDim.x;
+                if (i < R) {
+                    const int c = P * J > 1 ? (int)__umulhi((uint32_t)i, pj_magic) : i;   // (ceil(2^32 / 1) does not fit)
+                    const V3<float> h = back_project<float>(camF + 9 * c, q[u].x, q[u].y);
+                    const float cc = dot3(h, h);
+                    rays[i] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
+                    scs[i] = sv[u];
+                }
+            }
         }
     }
     __syncthreads();
-    const int tpp = (P + kTile - 1) / kTile;
-    const int items = a.npairs * tpp * tpp;
-    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, tb.pairs, rays, scs, kf, sf, f, it, lane);
+    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, idesc[it], rays, scs, kf, sf, f, lane);
 }
 
 // Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident
@@ -305,8 +349,8 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) gen_match_global_kernel(con
     if (item >= (long long)a.F * per_frame) return;
     const int f = (int)(item / per_frame), it = (int)(item - (long long)f * per_frame);
     const size_t R = (size_t)a.C * a.P * a.J;
-    gen_match_item(a, tb.camD, tb.pairs, rays + (size_t)f * R, a.scores + (size_t)f * R,
-                   reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f, it, lane);
+    gen_match_item(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, it), rays + (size_t)f * R, a.scores + (size_t)f * R,
+                   reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f, lane);
 }
 
 }  // namespace snowtri
