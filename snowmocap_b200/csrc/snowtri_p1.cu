@@ -142,8 +142,8 @@ static int run_p1_c(snowtri_t* h, const float* d_kpts, const float* d_scores, co
                 h->last_fly = 4;
                 return SNOWTRI_OK;
             }
-            h->p1_fast_fn = nullptr;
         }
+        h->p1_fast_fn = nullptr;   // the cache below may evict (unload) the module the shortcut points at
         char buf[256];
         std::string src = "#define P1_JIT 1\n";
         // Items per lane and resident CTAs per SM of the specialised build.  With the constants out of the register
