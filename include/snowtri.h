@@ -93,9 +93,10 @@ int snowtri_run(snowtri_t* h, const float* d_kpts, const float* d_scores, const 
                 float* d_out, float* d_pscores, int* d_nout, void* stream);
 
 /* Same through HOST buffers (pinned memory recommended).  The batch is cut into chunks that flow
- * through two internal streams (ordered after `stream`): chunk i's results travel device->host while
- * chunk i+1's inputs travel host->device and are triangulated, so both PCIe directions stay busy.
- * Returns after everything has arrived.  This is the call a reference-side plugin makes. */
+ * through three internal streams (ordered after `stream`) -- host->device copies, kernels,
+ * device->host copies: chunk i is triangulated and its results travel device->host while the inputs
+ * of the chunks behind it travel host->device, so both PCIe directions stay busy and never wait for
+ * a kernel.  Returns after everything has arrived.  This is the call a reference-side plugin makes. */
 int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, const int* h_counts,
                      int F, int P, int J, int keypoint_num, int Pout,
                      float* h_out, float* h_pscores, int* h_nout, void* stream);
@@ -108,7 +109,8 @@ int snowtri_run_host(snowtri_t* h, const float* h_kpts, const float* h_scores, c
 int snowtri_set_jit(snowtri_t* h, int mode);
 const char* snowtri_jit_status(snowtri_t* h);
 
-/* Frames per chunk of snowtri_run_host's copy/compute pipeline (0 = automatic, about 24 MB of input). */
+/* Frames per chunk of snowtri_run_host's copy/compute pipeline (0 = automatic: about 24 MB of input, and
+ * with several persons per camera at least eight frames per SM). */
 int snowtri_set_pipeline(snowtri_t* h, int frames_per_chunk);
 
 /* Human_Triangulation alone (reference snowvision/triangulation.py:50-93), float64 results.
