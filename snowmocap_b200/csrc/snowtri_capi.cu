@@ -64,6 +64,7 @@ extern "C" int snowtri_create(snowtri_t** out, int device, int C, const double* 
                     prop.major, prop.minor);
     }
     h->sm_count = prop.multiProcessorCount;
+    h->total_mem = (size_t)prop.totalGlobalMem;
     h->max_smem = (int)prop.sharedMemPerBlockOptin;
     h->smem_per_sm = (int)prop.sharedMemPerMultiprocessor;
     double* cam = (double*)malloc(sizeof(double) * 12 * C);

@@ -111,6 +111,22 @@ __device__ __forceinline__ int cluster_warp(int N, const uint32_t* klist, const 
 
 // Same greedy clustering by the WHOLE CTA (large candidate counts, one frame at a time).
 // wtmp: 2*NW+4 ints of scratch.  Must be called by all NT threads; returns K to every thread.
+// The per-warp counts of a CTA pass (wcnt[NW], NW <= 32): `off` = sum over the warps before `warp`, `tot` = sum over all.
+// Every warp scans the NW counts with its own lanes (5 shuffle steps) instead of every thread walking the array.
+template <int NW>
+__device__ __forceinline__ void cluster_warp_prefix(const int* wcnt, int warp, int lane, int& off, int& tot) {
+    static_assert(NW <= 32, "one lane per warp of the CTA");
+    const int c = lane < NW ? wcnt[lane] : 0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += up;
+    }
+    off = __shfl_sync(kFull, incl - c, warp);
+    tot = __shfl_sync(kFull, incl, 31);
+}
+
 template <int NT>
 __device__ int cluster_block(int ncand, const unsigned char* keep, uint32_t* klist, const double* cen,
                              unsigned char* ab, uint32_t* memb, int* cstart, int* cn, int* wtmp, double tol2,
@@ -129,12 +145,9 @@ __device__ int cluster_block(int ncand, const unsigned char* keep, uint32_t* kli
         const unsigned b = __ballot_sync(kFull, k);
         if (lane == 0) wcnt[warp] = __popc(b);
         __syncthreads();
-        int off = base, tot = 0;
-        for (int w = 0; w < NW; ++w) {
-            const int c = wcnt[w];
-            if (w < warp) off += c;
-            tot += c;
-        }
+        int off, tot;
+        cluster_warp_prefix<NW>(wcnt, warp, lane, off, tot);
+        off += base;
         if (k) {
             klist[off + __popc(b & lt)] = (uint32_t)i;
             ab[off + __popc(b & lt)] = 0;
@@ -170,13 +183,11 @@ __device__ int cluster_block(int ncand, const unsigned char* keep, uint32_t* kli
                 wmin[warp] = bl ? (r0 + warp * 32 + __ffs(bl) - 1) : N;
             }
             __syncthreads();
-            int off = 0, tot = 0, mn = N;
-            for (int w = 0; w < NW; ++w) {
-                const int c = wcnt[w];
-                if (w < warp) off += c;
-                tot += c;
-                mn = min(mn, wmin[w]);
-            }
+            int off, tot;
+            cluster_warp_prefix<NW>(wcnt, warp, lane, off, tot);
+            int mn = lane < NW ? wmin[lane] : N;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(kFull, mn, o));
             if (take) {
                 memb[mpos0 + 1 + taken + off + __popc(bt & lt)] = klist[i];
                 ab[i] = 1;

@@ -139,7 +139,12 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     // + kcount, + row descriptors (16 B per output slot), + rays (16 B each) for the large-rig match kernel
     const size_t nc = (size_t)(a.ncand > 0 ? a.ncand : 1);
     const size_t per_frame = nc * 50 + 4 + (fuse2 ? (size_t)Pout * 16 : 0) + (match_glob ? R * 16 : 0);
-    const size_t budget = (size_t)384 << 20;
+    // Scratch budget: a chunk should hold enough frames to fill the device with frame-per-CTA kernels.  At 384 MB,
+    // BASELINE configs[4] (7.4 MB of scratch per frame) ran 50-frame chunks: the clustering kernel had 50 CTAs on 148 SMs
+    // and took 48 % of the step (profiles/r2w).  A thirty-second of the device memory, between 384 MB and 4 GB.
+    size_t budget = h->total_mem / 32;
+    if (budget < ((size_t)384 << 20)) budget = (size_t)384 << 20;
+    if (budget > ((size_t)4 << 30)) budget = (size_t)4 << 30;
     long long fc_max = (long long)(budget / per_frame);
     if (fc_max < 1) fc_max = 1;
     if (fc_max > F) fc_max = F;
@@ -250,7 +255,8 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
             h->launches += 2;
         }
         // ---- ordered compaction + greedy clustering (+ member decode and row descriptors for the new fuse)
-        if (a.ncand > 64) gen_cluster_block_kernel<<<fc, 256, 0, st>>>(a);
+        if (a.ncand > 16384) gen_cluster_block_kernel<1024><<<fc, 1024, 0, st>>>(a);   // (7 680 candidates: 256 threads 0.43 ms, 1 024 threads 0.68 ms per 2 000 frames; 126 976: 1 024 threads 2.4x faster)
+        else if (a.ncand > 64) gen_cluster_block_kernel<256><<<fc, 256, 0, st>>>(a);
         else gen_cluster_warp_kernel<<<(fc + kGenWarps - 1) / kGenWarps, kGenWarps * 32, 0, st>>>(a);
         h->launches += 1;
         // ---- fuse + person score + persons per frame

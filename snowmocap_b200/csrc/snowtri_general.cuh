@@ -310,17 +310,19 @@ __device__ __forceinline__ void gen_describe(const GenArgs& a, int f, int K, int
 
 // ---- K2 ------------------------------------------------------------------------------------------------------
 // Large candidate counts: one CTA per frame.
-__global__ void __launch_bounds__(256) gen_cluster_block_kernel(const __grid_constant__ GenArgs a) {
-    __shared__ int wtmp[2 * 8 + 4];
+template <int NT>  // 256 threads, or 1024 for frames with thousands of candidates: the greedy loop is a chain of sweeps over
+                   // the remaining candidates, two CTA barriers per NT of them
+__global__ void __launch_bounds__(NT) gen_cluster_block_kernel(const __grid_constant__ GenArgs a) {
+    __shared__ int wtmp[2 * (NT / 32) + 4];
     const int f = blockIdx.x;
     const size_t o = (size_t)f * a.ncand;
-    const int K = cluster_block<256>(a.ncand, a.keep + o, a.klist + o, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o,
-                                     a.cn + o, wtmp, a.tol2, a.prm.num_tol);
+    const int K = cluster_block<NT>(a.ncand, a.keep + o, a.klist + o, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o,
+                                    a.cn + o, wtmp, a.tol2, a.prm.num_tol);
     if (threadIdx.x == 0) a.kcount[f] = K;
     if (a.tile_counter && blockIdx.x == 0 && threadIdx.x == 0) *a.tile_counter = 0;
     if (a.memb2) {  // cluster_block ends with a barrier: the lists are visible to the whole CTA
         __syncthreads();
-        gen_describe(a, f, K, threadIdx.x, 256);
+        gen_describe(a, f, K, threadIdx.x, NT);
     }
 }
 

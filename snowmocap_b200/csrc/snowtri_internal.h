@@ -21,6 +21,7 @@ char* snowtri_global_error();  // message buffer used when there is no handle (c
 
 struct snowtri_handle {
     int device, C, sm_count, max_smem;
+    size_t total_mem;         // device memory (sizes the scratch of the several-persons path)
     double* d_cam;  // (C,12) M = R*inv(K), t
     double* cam_host;
     double* kinv_host;  // (C,9) inverse intrinsics and (C,9) camera->world rotations, kept for the DLT mode
