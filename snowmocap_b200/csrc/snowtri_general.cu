@@ -133,7 +133,12 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     const size_t mtab = MatchTables::bytes(C, a.npairs);
     const size_t mstaged = mtab + match_desc_bytes(a.npairs * ((P + kTile - 1) / kTile) * ((P + kTile - 1) / kTile)) + match_camf_bytes(C) + R * 20;   // item descriptors, rays (16 B) + scores (4 B) of one frame
     const bool match_smem = match2 && !h->no_fly && mstaged <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024;  // two CTAs per SM
-    const bool match_glob = match2 && !match_smem;
+    // a camera pair's 2 P rows staged per CTA (two CTAs per SM), when the whole frame does not fit
+    const size_t mpair = mtab + 80 + (size_t)2 * P * J * 20;
+    const char* env_pairk = getenv("SNOWTRI_MATCH_PAIR");   // experiments: 0 = rays from the scratch array
+    const bool match_pair = match2 && !match_smem && !h->no_fly && mpair <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024 &&
+                            !(env_pairk && atoi(env_pairk) == 0);
+    const bool match_glob = match2 && !match_smem && !match_pair;
 
     // scratch per frame: keep, ab (1 B), cen (24 B), klist, memb, cstart, cn (4 B each), memb2 (8 B) per candidate,
     // + kcount, + row descriptors (16 B per output slot), + rays (16 B each) for the large-rig match kernel
@@ -209,6 +214,17 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
                 if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "gen_match_smem_kernel attribute: %s", cudaGetErrorString(e));
                 gen_match_smem_kernel<<<fc, nw * 32, mstaged, st>>>(a);
                 last_grid = fc;
+                h->launches += 1;
+            } else if (match_pair) {
+                const int tiles = tpp * tpp;
+                const int nw = tiles >= 8 ? 8 : (tiles < 4 ? 4 : tiles);   // at least four warps for the ray build
+                const long long blocks = (long long)fc * a.npairs;
+                if (blocks > 0x7fffffffLL) return fail(h, SNOWTRI_E_UNSUPPORTED, "snowtri_run: batch too large");
+                cudaError_t e = cudaFuncSetAttribute(gen_match_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     (int)(mpair > 49152 ? mpair : 49152));
+                if (e != cudaSuccess) return fail(h, SNOWTRI_E_CUDA, "gen_match_pair_kernel attribute: %s", cudaGetErrorString(e));
+                gen_match_pair_kernel<<<(unsigned)blocks, nw * 32, mpair, st>>>(a);
+                last_grid = (int)blocks;
                 h->launches += 1;
             } else {
                 const size_t rtab = (size_t)C * 9 * 4;

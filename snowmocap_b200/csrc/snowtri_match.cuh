@@ -100,7 +100,10 @@ __device__ __forceinline__ MatchItemDesc match_item_desc(const GenArgs& a, const
     return q;
 }
 
-__device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const MatchItemDesc& q, const float4* rays, const float* scs, int f) {
+// `slot_m` / `slot_s`: which block of P rows of `rays` / `scs` holds the main / secondary camera (the camera index when the
+// arrays hold the whole frame, 0 / 1 when a CTA staged just its camera pair)
+__device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const MatchItemDesc& q, const float4* rays, const float* scs, int f,
+                                                   int slot_m = -1, int slot_s = -1) {
     const int C = a.C, P = a.P, J = a.J;
     MatchItem t;
     t.pair = q.pair;
@@ -115,10 +118,11 @@ __device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const Match
     t.d.x = q.dx;
     t.d.y = q.dy;
     t.d.z = q.dz;
-    t.rm = rays + (size_t)(t.mc * P + t.pm0) * J;
-    t.rs = rays + (size_t)(t.sc * P + t.ps0) * J;
-    t.qm = scs + (size_t)(t.mc * P + t.pm0) * J;
-    t.qs = scs + (size_t)(t.sc * P + t.ps0) * J;
+    const int bm = slot_m < 0 ? t.mc : slot_m, bs = slot_s < 0 ? t.sc : slot_s;
+    t.rm = rays + (size_t)(bm * P + t.pm0) * J;
+    t.rs = rays + (size_t)(bs * P + t.ps0) * J;
+    t.qm = scs + (size_t)(bm * P + t.pm0) * J;
+    t.qs = scs + (size_t)(bs * P + t.ps0) * J;
     return t;
 }
 
@@ -245,8 +249,9 @@ __device__ __forceinline__ void match_decide(const GenArgs& a, const double* cam
 // Also dropped: the leftover joints split over the lanes (32 / tail lanes per joint, 3 evaluations per lane): 4.8 %
 // fewer instructions, but the short dependent tail issues at 70.6 % instead of 74.8 % -- 1.089 vs 1.079 ms, profiles/r2t.
 __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const MatchItemDesc& q, const float4* rays,
-                                               const float* scs, const float2* kf, const float* sf, int f, int lane) {
-    const MatchItem t = match_item_of(a, q, rays, scs, f);
+                                               const float* scs, const float2* kf, const float* sf, int f, int lane,
+                                               int slot_m = -1, int slot_s = -1) {
+    const MatchItem t = match_item_of(a, q, rays, scs, f, slot_m, slot_s);
     const bool sums = !a.all_kept && t.nm > 0 && t.ns > 0;
     float lo_tot = 0.f, hi_tot = 0.f;
     if (sums) {
@@ -334,6 +339,60 @@ __global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_con
     }
     __syncthreads();
     for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, idesc[it], rays, scs, kf, sf, f, lane);
+}
+
+// Large rigs, where a frame's rays do not fit in shared memory but the 2 P rows of ONE camera pair do (20 bytes per ray:
+// 43 KB at 8 persons x 133 joints, 85 KB at 16): one CTA per (frame, camera pair) builds the rays of its two cameras from
+// the raw inputs (L2-resident while the frame's C(C-1)/2 CTAs run: consecutive block indices) and its warps walk the
+// pair's person tiles out of shared memory.  Against gen_match_global_kernel (rays from a scratch array in L2 at every
+// pass): 4.87 -> see DESIGN.md ns per item at BASELINE configs[3].
+__global__ void __launch_bounds__(256, 2) gen_match_pair_kernel(const __grid_constant__ GenArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    MatchTables tb(smem, a);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = blockDim.x >> 5;
+    const int C = a.C, P = a.P, J = a.J, PJ = P * J;
+    const int f = blockIdx.x / a.npairs, pair = blockIdx.x - f * a.npairs;
+    const size_t R = (size_t)C * PJ;
+    float* camF = reinterpret_cast<float*>(smem + MatchTables::bytes(C, a.npairs));  // M of the two cameras, float32
+    float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs) + 80);
+    float* scs = reinterpret_cast<float*>(rays + 2 * PJ);
+    const float2* kf = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R;
+    const float* sf = a.scores + (size_t)f * R;
+    int mc, sc;
+    decode_pair(pair, C, mc, sc);
+    if (threadIdx.x < 18) {
+        const int c = threadIdx.x < 9 ? mc : sc, i = threadIdx.x < 9 ? threadIdx.x : threadIdx.x - 9;
+        camF[threadIdx.x] = (float)a.cam[12 * c + i];
+    }
+    __syncthreads();  // tables, camF
+    {
+        constexpr int NB = 8;
+        for (int i0 = threadIdx.x; i0 < 2 * PJ; i0 += NB * blockDim.x) {
+            float2 q[NB];
+            float sv[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int i = min(i0 + u * (int)blockDim.x, 2 * PJ - 1);
+                const int src = i < PJ ? mc * PJ + i : sc * PJ + (i - PJ);
+                q[u] = __ldg(kf + src);
+                sv[u] = __ldg(sf + src);
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int i = i0 + u * (int)blockDim.x;
+                if (i < 2 * PJ) {
+                    const V3<float> h = back_project<float>(camF + (i < PJ ? 0 : 9), q[u].x, q[u].y);
+                    const float cc = dot3(h, h);
+                    rays[i] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
+                    scs[i] = sv[u];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int tpp = (P + kTile - 1) / kTile;
+    for (int tt = warp; tt < tpp * tpp; tt += NW)
+        gen_match_item(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, pair * tpp * tpp + tt), rays, scs, kf, sf, f, lane, 0, 1);
 }
 
 // Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident
