@@ -131,10 +131,11 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     const bool fuse2 = gen2 && C >= 2 && C <= 8 && Pout <= 32 && P <= 255;
     const size_t R = (size_t)C * P * J;
     const size_t mtab = MatchTables::bytes(C, a.npairs);
-    const size_t mstaged = mtab + match_desc_bytes(a.npairs * ((P + kTile - 1) / kTile) * ((P + kTile - 1) / kTile)) + match_camf_bytes(C) + R * 20;   // item descriptors, rays (16 B) + scores (4 B) of one frame
+    const size_t mstaged = mtab + match_desc_bytes(a.npairs * ((P + kTile - 1) / kTile) * ((P + kTile - 1) / kTile)) + match_camf_bytes(C) +
+                           (MATCH_JM ? match_jm_bytes(C, P, J) : R * 20);   // item descriptors, rays (16 B) + scores (4 B) of one frame
     const bool match_smem = match2 && !h->no_fly && mstaged <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024;  // two CTAs per SM
     // a camera pair's 2 P rows staged per CTA (two CTAs per SM), when the whole frame does not fit
-    const size_t mpair = mtab + 80 + (size_t)2 * P * J * 20;
+    const size_t mpair = mtab + 80 + (MATCH_JM ? match_jm_bytes(2, P, J) : (size_t)2 * P * J * 20);
     const char* env_pairk = getenv("SNOWTRI_MATCH_PAIR");   // experiments: 0 = rays from the scratch array
     const bool match_pair = match2 && !match_smem && !h->no_fly && mpair <= ((size_t)h->smem_per_sm - 2048) / 2 - 1024 &&
                             !(env_pairk && atoi(env_pairk) == 0);

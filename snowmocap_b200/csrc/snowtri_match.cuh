@@ -67,8 +67,31 @@ __device__ __forceinline__ float reduce16(float (&v)[16], int lane) {
 
 // One (frame, camera pair, 4 x 4 person tile) item as a lane sees it (warp-uniform in the main loop; in the tail
 // pass every group of lanes looks at another item).
+// Joint-major staging of the rays of a CTA (MATCH_JM): element (joint j, camera slot b, person p) of `rays` lives at
+// j * rw_r + b * ppad + p and of `scs` at j * rw_s + b * ppad + p, ppad = P rounded up to 4.  The 4 + 4 rays a lane needs
+// for its joint are then two runs of consecutive float4 (constant offsets from one address per side instead of eight
+// row addresses that depend on J: 38 -> 12 address instructions per pass) and the 4 scores of a side are one 128-bit
+// load.  rw_r is odd and rw_s is 4 x odd, so that the 128-bit loads of consecutive joints (and the stores of the ray
+// build, a thread per ray along j) fall into different banks.  rw_r == 0: row-major ([row][j]; the scratch-array kernel).
+struct MatchLayout {
+    int rw_r, rw_s, ppad;
+};
+__host__ __device__ inline MatchLayout match_layout_jm(int slots, int P) {
+    MatchLayout l;
+    l.ppad = (P + 3) & ~3;
+    const int rw = slots * l.ppad;
+    l.rw_r = rw | 1;
+    l.rw_s = ((rw / 4) | 1) * 4;
+    return l;
+}
+__host__ __device__ inline size_t match_jm_bytes(int slots, int P, int J) {
+    const MatchLayout l = match_layout_jm(slots, P);
+    return (size_t)J * ((size_t)l.rw_r * 16 + (size_t)l.rw_s * 4) + 16;
+}
+
 struct MatchItem {
     int pair, mc, sc, pm0, ps0, nm, ns;  // nm / ns: persons of the tile that are present
+    int rw_r, rw_s;                      // joint-major strides (0: row-major)
     V3<float> d;                         // ts - tm
     const float4 *rm, *rs;               // rays of the tile's first main / secondary person
     const float *qm, *qs;                // their scores
@@ -103,7 +126,7 @@ __device__ __forceinline__ MatchItemDesc match_item_desc(const GenArgs& a, const
 // `slot_m` / `slot_s`: which block of P rows of `rays` / `scs` holds the main / secondary camera (the camera index when the
 // arrays hold the whole frame, 0 / 1 when a CTA staged just its camera pair)
 __device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const MatchItemDesc& q, const float4* rays, const float* scs, int f,
-                                                   int slot_m = -1, int slot_s = -1) {
+                                                   int slot_m = -1, int slot_s = -1, MatchLayout lay = MatchLayout{0, 0, 0}) {
     const int C = a.C, P = a.P, J = a.J;
     MatchItem t;
     t.pair = q.pair;
@@ -119,10 +142,19 @@ __device__ __forceinline__ MatchItem match_item_of(const GenArgs& a, const Match
     t.d.y = q.dy;
     t.d.z = q.dz;
     const int bm = slot_m < 0 ? t.mc : slot_m, bs = slot_s < 0 ? t.sc : slot_s;
-    t.rm = rays + (size_t)(bm * P + t.pm0) * J;
-    t.rs = rays + (size_t)(bs * P + t.ps0) * J;
-    t.qm = scs + (size_t)(bm * P + t.pm0) * J;
-    t.qs = scs + (size_t)(bs * P + t.ps0) * J;
+    t.rw_r = lay.rw_r;
+    t.rw_s = lay.rw_s;
+    if (lay.rw_r) {
+        t.rm = rays + bm * lay.ppad + t.pm0;
+        t.rs = rays + bs * lay.ppad + t.ps0;
+        t.qm = scs + bm * lay.ppad + t.pm0;
+        t.qs = scs + bs * lay.ppad + t.ps0;
+    } else {
+        t.rm = rays + (size_t)(bm * P + t.pm0) * J;
+        t.rs = rays + (size_t)(bs * P + t.ps0) * J;
+        t.qm = scs + (size_t)(bm * P + t.pm0) * J;
+        t.qs = scs + (size_t)(bs * P + t.ps0) * J;
+    }
     return t;
 }
 
@@ -242,16 +274,117 @@ __device__ __forceinline__ void match_decide(const GenArgs& a, const double* cam
     }
 }
 
+// Second form of the same bounds (MATCH_SUMS, the default): with t = kDistDelta/dist the two bounds are
+//   lower = sum w (1 - t) = S1 - kDistDelta S2,   upper = sum w (1 + 2t) = S1 + 2 kDistDelta S2 + band,
+//   S1 = sum w,  S2 = sum w/dist   over the joints that surely pass the gate with t <= 1/2,
+// so a candidate needs two running sums and no per-joint selects (27 -> 23 instructions per evaluation).  What the
+// sums leave out:
+//   * a joint whose gate sits inside its guard band adds at most kappa (sm + ss) to the upper bound, kappa =
+//     r_sure (1 + 2 kDistDelta r_sure): the lane counts such joints (`nband`, all 16 candidates of the tile together)
+//     and the tile's upper bounds all get  kappa * sum over lanes of nband * max(sm + ss)  -- a fraction of a joint's
+//     score, against thresholds of J joint scores;
+//   * a joint with t > 1/2 (rays that pass within 0.02 mm) has no upper bound: it sets the candidate's bit in `wild`
+//     (one register per lane for the 16 candidates) and the candidate's upper bound is +inf.
+// The running maximum of sm + ss (`qmax`) is taken over every ray of the pass, counted or not.
+// FULL: all 4 + 4 persons of the tile are present (warp-uniform; the usual case) -- no row selects, no count tests.
+template <bool FULL, bool JM>
+__device__ __forceinline__ void match_eval_sums(const MatchItem& t, int J, int j, bool valid, const MatchGate& g,
+                                                float (&s1)[kTile * kTile], float (&s2)[kTile * kTile], unsigned& wild,
+                                                unsigned& nband, float& qmax) {
+    float4 m[kTile], s[kTile];
+    float sm[kTile], ss[kTile], lim_sure[kTile], lim_maybe[kTile];
+    const float4 *pm = t.rm, *ps = t.rs;
+    const float *qm = t.qm, *qs = t.qs;
+    if constexpr (JM) {
+        pm += j * t.rw_r; ps += j * t.rw_r;
+        qm += j * t.rw_s; qs += j * t.rw_s;
+        if constexpr (FULL) {
+            const float4 a4 = *reinterpret_cast<const float4*>(qm), b4 = *reinterpret_cast<const float4*>(qs);
+            sm[0] = a4.x; sm[1] = a4.y; sm[2] = a4.z; sm[3] = a4.w;
+            ss[0] = b4.x; ss[1] = b4.y; ss[2] = b4.z; ss[3] = b4.w;
+        }
+    } else {
+        pm += j; ps += j;
+        qm += j; qs += j;
+    }
+    const int rstride = JM ? 1 : J;
+#pragma unroll
+    for (int i = 0; i < kTile; ++i) {  // persons beyond the count alias person 0 of the tile and are masked
+        const int r = (FULL || i < t.nm) ? i : 0;
+        m[i] = pm[(size_t)r * rstride];
+        if constexpr (!(JM && FULL)) sm[i] = qm[(size_t)r * rstride];
+    }
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) {
+        const int r = (FULL || k < t.ns) ? k : 0;
+        s[k] = ps[(size_t)r * rstride];
+        if constexpr (!(JM && FULL)) ss[k] = qs[(size_t)r * rstride];
+        // a secondary ray with a low score (it carries -|hs|^2) or beyond the count is gated through its limits
+        const bool oks = (FULL || k < t.ns) && !(s[k].w < 0.f);
+        lim_sure[k] = oks ? g.r_sure : INFINITY;
+        lim_maybe[k] = oks ? g.r_maybe : INFINITY;
+        s[k].w = fabsf(s[k].w);
+    }
+    qmax = fmaxf(qmax, fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3])) + fmaxf(fmaxf(ss[0], ss[1]), fmaxf(ss[2], ss[3])));
+    constexpr float kTight = 0.5f / kDistDelta;
+#pragma unroll
+    for (int i = 0; i < kTile; ++i) {
+        // a main ray that does not count (idle lane, person beyond the count, score below the keypoint threshold) gets
+        // 1/dist = -inf: it fails every test below without a predicate of its own
+        const float pen = (valid && (FULL || i < t.nm) && !(m[i].w < 0.f)) ? 0.f : INFINITY;
+        m[i].w = fabsf(m[i].w);
+        V3<float> e;  // d x hm:  d.(hm x hs) = hs.(d x hm)
+        e.x = fmaf(t.d.y, m[i].z, -(t.d.z * m[i].y));
+        e.y = fmaf(t.d.z, m[i].x, -(t.d.x * m[i].z));
+        e.z = fmaf(t.d.x, m[i].y, -(t.d.y * m[i].x));
+#pragma unroll
+        for (int k = 0; k < kTile; ++k) {
+            const float B = fmaf(m[i].x, s[k].x, fmaf(m[i].y, s[k].y, m[i].z * s[k].z));
+            const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
+            const float nn = fmaf(m[i].w, s[k].w, -(B * B));   // |hm x hs|^2
+            const float rd = fmaf(nn, rsqrt_fast(nn * (dn * dn)), -pen);  // sqrt(n.n)/|d.n| = 1/dist
+            const float w = (sm[i] + ss[k]) * rd;              // score / 0.0005
+            // dist > dthr is gated (strict); a NaN distance is not (Q8/Q9): it passes the tests and poisons the sums.
+            //   pass = !(rd < lim_sure);  sure = pass && !(rd > kTight);  wild = pass && rd > kTight;
+            //   band = !pass && !(rd < lim_maybe)
+            // Predicated straight-line code: written in C++ the compiler branches around the tests and every evaluation
+            // becomes its own basic block.
+            asm("{\n\t.reg .pred pp, pq, ps, pw, pb;\n\t"
+                "setp.geu.f32 pp|pq, %4, %5;\n\t"
+                "setp.leu.and.f32 ps|pw, %4, %7, pp;\n\t"
+                "setp.geu.and.f32 pb, %4, %6, pq;\n\t"
+                "@ps add.f32 %0, %0, %8;\n\t"
+                "@ps fma.rn.f32 %1, %8, %4, %1;\n\t"
+                "@pw or.b32 %2, %2, %9;\n\t"
+                "@pb add.u32 %3, %3, 1;\n\t}"
+                : "+f"(s1[i * kTile + k]), "+f"(s2[i * kTile + k]), "+r"(wild), "+r"(nband)
+                : "f"(rd), "f"(lim_sure[k]), "f"(lim_maybe[k]), "f"(kTight), "f"(w), "r"(1u << (i * kTile + k)));
+        }
+    }
+}
+
+#ifndef MATCH_SUMS
+#define MATCH_SUMS 1
+#endif
+#ifndef MATCH_JM
+#define MATCH_JM MATCH_SUMS   // joint-major staging needs the second form of the evaluation
+#endif
+template <bool V>
+struct MBool {
+    static constexpr bool value = V;
+};
+
 // One item by one warp, joints in chunks of 32 (the last one partly idle: 5 of 32 lanes at 133 joints).  Tried and
 // dropped: the leftover joints of four items sharing one pass -- 11 % fewer instructions, but either the unrolled form
 // outgrows the instruction cache (1.33 -> 1.47 ms at BASELINE configs[2]) or the rolled form pays the saving back in
 // index arithmetic and needs more than the 128 registers two 7-warp CTAs per SM leave (2.03 ms); profiles/r2d, r2e.
 // Also dropped: the leftover joints split over the lanes (32 / tail lanes per joint, 3 evaluations per lane): 4.8 %
 // fewer instructions, but the short dependent tail issues at 70.6 % instead of 74.8 % -- 1.089 vs 1.079 ms, profiles/r2t.
+template <bool JM>
 __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* camD, const MatchItemDesc& q, const float4* rays,
                                                const float* scs, const float2* kf, const float* sf, int f, int lane,
-                                               int slot_m = -1, int slot_s = -1) {
-    const MatchItem t = match_item_of(a, q, rays, scs, f, slot_m, slot_s);
+                                               int slot_m = -1, int slot_s = -1, MatchLayout lay = MatchLayout{0, 0, 0}) {
+    const MatchItem t = match_item_of(a, q, rays, scs, f, slot_m, slot_s, lay);
     const bool sums = !a.all_kept && t.nm > 0 && t.ns > 0;
     float lo_tot = 0.f, hi_tot = 0.f;
     if (sums) {
@@ -259,12 +392,35 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
         float lo[kTile * kTile], hi[kTile * kTile];
 #pragma unroll
         for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
+#if MATCH_SUMS
+        unsigned wild = 0u, nband = 0u;
+        float qmax = 0.f;
+        auto passes = [&](auto fullc, auto jmc) {
+            for (int j0 = 0; j0 < a.J; j0 += 32) {
+                const bool valid = j0 + lane < a.J;
+                match_eval_sums<decltype(fullc)::value, decltype(jmc)::value>(t, a.J, valid ? j0 + lane : a.J - 1, valid, g, lo, hi, wild, nband, qmax);
+            }
+        };
+        const bool full = t.nm == kTile && t.ns == kTile;
+        if (full) passes(MBool<true>{}, MBool<JM>{});
+        else passes(MBool<false>{}, MBool<JM>{});
+        const float S1 = reduce16(lo, lane), S2 = reduce16(hi, lane);
+        wild = __reduce_or_sync(kFull, wild);
+        // guard-band joints of the whole tile, charged to every candidate; 1.001: float32 rounding of this small term
+        // (a threshold below 2 kDistDelta puts the band itself beyond t = 1/2: no bound)
+        const float bsum = warp_sum((float)nband * qmax);
+        const float kappa = g.r_sure <= 0.5f / kDistDelta ? g.r_sure * fmaf(2.f * kDistDelta, g.r_sure, 1.f) * 1.001f : INFINITY;
+        const float band = bsum > 0.f ? bsum * kappa : 0.f;
+        lo_tot = fmaf(-kDistDelta, S2, S1);
+        hi_tot = ((wild >> ((lane >> 1) & 15)) & 1u) ? INFINITY : fmaf(2.f * kDistDelta, S2, S1) + band;
+#else
         for (int j0 = 0; j0 < a.J; j0 += 32) {
             const bool valid = j0 + lane < a.J;
             match_eval(t, a.J, valid ? j0 + lane : a.J - 1, valid, g, lo, hi);
         }
         lo_tot = reduce16(lo, lane);
         hi_tot = reduce16(hi, lane);
+#endif
     }
     match_decide(a, camD, kf, sf, f, t, sums, lo_tot, hi_tot, lane);
 }
@@ -302,7 +458,13 @@ __global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_con
     MatchItemDesc* idesc = reinterpret_cast<MatchItemDesc*>(smem + MatchTables::bytes(C, a.npairs));
     float* camF = reinterpret_cast<float*>(smem + MatchTables::bytes(C, a.npairs) + match_desc_bytes(items));  // M of every camera, float32
     float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs) + match_desc_bytes(items) + match_camf_bytes(C));
+#if MATCH_JM
+    const MatchLayout lay = match_layout_jm(C, P);
+    float* scs = reinterpret_cast<float*>(rays + (size_t)J * lay.rw_r);
+#else
+    const MatchLayout lay{0, 0, 0};
     float* scs = reinterpret_cast<float*>(rays + R);
+#endif
     const float2* kf = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R;
     const float* sf = a.scores + (size_t)f * R;
     for (int i = threadIdx.x; i < C * 9; i += blockDim.x) camF[i] = (float)a.cam[(i / 9) * 12 + (i % 9)];
@@ -315,6 +477,7 @@ __global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_con
     {
         constexpr int NB = 8;
         const uint32_t pj_magic = (uint32_t)((0x100000000ull + (uint32_t)(P * J) - 1u) / (uint32_t)(P * J));  // exact: C (P J)^2 < 2^32 here
+        const uint32_t j_magic = (uint32_t)((0x100000000ull + (uint32_t)J - 1u) / (uint32_t)J);
         for (int i0 = threadIdx.x; i0 < R; i0 += NB * blockDim.x) {
             float2 q[NB];
             float sv[NB];
@@ -331,14 +494,20 @@ __global__ void __launch_bounds__(256, 2) gen_match_smem_kernel(const __grid_con
                     const int c = P * J > 1 ? (int)__umulhi((uint32_t)i, pj_magic) : i;   // (ceil(2^32 / 1) does not fit)
                     const V3<float> h = back_project<float>(camF + 9 * c, q[u].x, q[u].y);
                     const float cc = dot3(h, h);
-                    rays[i] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
-                    scs[i] = sv[u];
+                    int dr = i, ds = i;
+                    if (lay.rw_r) {
+                        const int rem = i - c * P * J, pp = J > 1 ? (int)__umulhi((uint32_t)rem, j_magic) : rem, jj = rem - pp * J;
+                        dr = jj * lay.rw_r + c * lay.ppad + pp;
+                        ds = jj * lay.rw_s + c * lay.ppad + pp;
+                    }
+                    rays[dr] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
+                    scs[ds] = sv[u];
                 }
             }
         }
     }
     __syncthreads();
-    for (int it = warp; it < items; it += NW) gen_match_item(a, tb.camD, idesc[it], rays, scs, kf, sf, f, lane);
+    for (int it = warp; it < items; it += NW) gen_match_item<(MATCH_JM != 0)>(a, tb.camD, idesc[it], rays, scs, kf, sf, f, lane, -1, -1, lay);
 }
 
 // Large rigs, where a frame's rays do not fit in shared memory but the 2 P rows of ONE camera pair do (20 bytes per ray:
@@ -355,7 +524,14 @@ __global__ void __launch_bounds__(256, 2) gen_match_pair_kernel(const __grid_con
     const size_t R = (size_t)C * PJ;
     float* camF = reinterpret_cast<float*>(smem + MatchTables::bytes(C, a.npairs));  // M of the two cameras, float32
     float4* rays = reinterpret_cast<float4*>(smem + MatchTables::bytes(C, a.npairs) + 80);
+#if MATCH_JM
+    const MatchLayout lay = match_layout_jm(2, P);
+    float* scs = reinterpret_cast<float*>(rays + (size_t)J * lay.rw_r);
+#else
+    const MatchLayout lay{0, 0, 0};
     float* scs = reinterpret_cast<float*>(rays + 2 * PJ);
+#endif
+    const uint32_t j_magic = (uint32_t)((0x100000000ull + (uint32_t)J - 1u) / (uint32_t)J);
     const float2* kf = reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R;
     const float* sf = a.scores + (size_t)f * R;
     int mc, sc;
@@ -383,8 +559,15 @@ __global__ void __launch_bounds__(256, 2) gen_match_pair_kernel(const __grid_con
                 if (i < 2 * PJ) {
                     const V3<float> h = back_project<float>(camF + (i < PJ ? 0 : 9), q[u].x, q[u].y);
                     const float cc = dot3(h, h);
-                    rays[i] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
-                    scs[i] = sv[u];
+                    int dr = i, ds = i;
+                    if (lay.rw_r) {
+                        const int slot = i < PJ ? 0 : 1, rem = i - slot * PJ;
+                        const int pp = J > 1 ? (int)__umulhi((uint32_t)rem, j_magic) : rem, jj = rem - pp * J;
+                        dr = jj * lay.rw_r + slot * lay.ppad + pp;
+                        ds = jj * lay.rw_s + slot * lay.ppad + pp;
+                    }
+                    rays[dr] = make_float4(h.x, h.y, h.z, sv[u] < a.prm.kst_f ? -cc : cc);
+                    scs[ds] = sv[u];
                 }
             }
         }
@@ -392,7 +575,7 @@ __global__ void __launch_bounds__(256, 2) gen_match_pair_kernel(const __grid_con
     __syncthreads();
     const int tpp = (P + kTile - 1) / kTile;
     for (int tt = warp; tt < tpp * tpp; tt += NW)
-        gen_match_item(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, pair * tpp * tpp + tt), rays, scs, kf, sf, f, lane, 0, 1);
+        gen_match_item<(MATCH_JM != 0)>(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, pair * tpp * tpp + tt), rays, scs, kf, sf, f, lane, 0, 1, lay);
 }
 
 // Any size: rays from the scratch array written by gen_rays_kernel, scores straight from the input (both L2-resident
@@ -408,7 +591,7 @@ __global__ void __launch_bounds__(kGenWarps * 32, 2) gen_match_global_kernel(con
     if (item >= (long long)a.F * per_frame) return;
     const int f = (int)(item / per_frame), it = (int)(item - (long long)f * per_frame);
     const size_t R = (size_t)a.C * a.P * a.J;
-    gen_match_item(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, it), rays + (size_t)f * R, a.scores + (size_t)f * R,
+    gen_match_item<false>(a, tb.camD, match_item_desc(a, tb.camD, tb.pairs, it), rays + (size_t)f * R, a.scores + (size_t)f * R,
                    reinterpret_cast<const float2*>(a.kpts) + (size_t)f * R, a.scores + (size_t)f * R, f, lane);
 }
 
