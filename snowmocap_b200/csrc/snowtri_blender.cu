@@ -26,6 +26,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "snowtri_internal.h"
 
 #define SNOWTRI_NCTRL 24
@@ -43,6 +45,10 @@ struct snowtri_blender_smooth_state {
     double* d_work;   // chunk-parallel path: per chunk 33 values per (person, control point), see kBsWork
     size_t work_chunks;
     int sequential;   // 1 = always the single-launch sequential kernel
+    int force_scan;   // 1 = long batches always take the chunk scan (pass A / B / C)
+    int coop_blocks;  // CTAs of blender_smooth_overlap_kernel a cooperative launch can hold (0: not asked yet, -1: none)
+    int forget[SNOWTRI_NCTRL];   // present frames after which a follower has forgotten its state (0: not within kBsMaxForget)
+    double forget_T;  // delta_time `forget` was computed for
 };
 
 namespace snowtri {
@@ -234,6 +240,7 @@ struct BlenderSmoothArgs {
     int F, Pout, P;
     double T, invT;
     double k1[SNOWTRI_NCTRL], inv_k2[SNOWTRI_NCTRL], k3[SNOWTRI_NCTRL];
+    int forget[SNOWTRI_NCTRL];   // one-pass path only
 };
 
 #ifndef BS_BATCH_BYTES
@@ -469,6 +476,144 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
     }
 }
 
+
+// ---- one-pass path: chunks with a warm-up instead of a hand-over (see smooth_overlap_kernel in snowtri_smooth.cu) -------
+// The (y, yd) part of a follower's state decays by the same 2x2 map on every present frame, valid or not; xp is
+// replaced by the input on a valid frame and kept on an invalid one.  So a (chunk, person, control point) thread that
+// starts from a ZERO state on a present, valid frame and then walks W present frames (|A^W| < 1e-19, W per control
+// point from its f, z, r) holds the exact state to the last bit of a float64 when it reaches its own chunk.  A thread
+// that runs out of history first (first chunk, absent person, a control point that stayed invalid) starts at frame 0
+// of the batch from the carried state: the sequential recurrence.  Cooperative launch: a grid-wide barrier separates
+// the warm-ups (they read frames of earlier chunks, which are smoothed in place) from the chunk walks.
+constexpr int kBsMaxForget = 256;
+
+template <bool B>
+struct BsBool {
+    static constexpr bool value = B;
+};
+
+template <typename V>
+__global__ void __launch_bounds__(96) blender_smooth_overlap_kernel(const BlenderSmoothArgs a, int L, int nchunks) {
+    const int NT = a.P * SNOWTRI_NCTRL;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gid < (long long)nchunks * NT;
+    const int chunk = active ? (int)(gid / NT) : 0, tid = active ? (int)(gid - (long long)chunk * NT) : 0;
+    const int k = tid / SNOWTRI_NCTRL, c = tid - k * SNOWTRI_NCTRL;
+    const bool was_init = a.state[0] != 0.0;
+    const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
+    const double k1 = a.k1[c], inv_k2 = a.inv_k2[c], k3 = a.k3[c];
+    V* ctrl = reinterpret_cast<V*>(a.ctrl);
+    const bool inrange = k < a.Pout;
+    const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
+    const size_t base = (size_t)(inrange ? k : 0) * SNOWTRI_NCTRL + c;
+    const size_t vbase = inrange ? k : 0;
+    const int t_begin = chunk * L, t_end = min(a.F, t_begin + L);
+    double xp[4] = {0, 0, 0, 0}, y[4] = {0, 0, 0, 0}, yd[4] = {0, 0, 0, 0};
+    constexpr int NB = kBsBatchBytes / (int)sizeof(V);
+    auto walk = [&](int t_from, int t_to, auto ownc) {
+        constexpr bool OWN = decltype(ownc)::value;
+        for (int t0 = t_from; t0 < t_to; t0 += NB) {
+            V buf[NB];
+            unsigned vb[NB];
+            int nb[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int t = min(t0 + u, t_to - 1);
+                buf[u] = ctrl[(size_t)t * stride + base];
+                vb[u] = a.valid[(size_t)t * a.Pout + vbase];
+                nb[u] = a.nout[t];
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int t = t0 + u;
+                if (t >= t_to) break;
+                const V p = buf[u];
+                const bool ok = (vb[u] >> c) & 1u;
+                const int n = min(max(nb[u], 0), a.Pout);
+                const double x[4] = {(double)p.x, (double)p.y, (double)p.z, (double)p.w};
+                if (!was_init && t == 0) {   // the seeding frame of a clip (blender.py:165-176)
+                    if (k < n0) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            xp[i] = y[i] = ok ? x[i] : 0.0;
+                            yd[i] = 0.0;
+                        }
+                    }
+                    if (OWN && tid == 0) a.nsm[t] = n;
+                    continue;
+                }
+                const int m = min(n, n0);
+                if (OWN && tid == 0) a.nsm[t] = m;
+                if (k < m) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) bs_step(a, k1, inv_k2, k3, ok, x[i], xp[i], y[i], yd[i]);
+                    if (OWN) {
+                        V o;
+                        o.x = (decltype(o.x))y[0];
+                        o.y = (decltype(o.x))y[1];
+                        o.z = (decltype(o.x))y[2];
+                        o.w = (decltype(o.x))y[3];
+                        ctrl[(size_t)t * stride + base] = o;
+                    }
+                }
+            }
+        }
+    };
+    if (active) {
+        // warm-up start: walking back, W present frames, then the next present frame whose control point is valid
+        int tw = t_begin, need = a.forget[c];
+        bool found = false;
+        while (tw > 0 && !found) {
+            int nb[8];
+            unsigned vb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = max(tw - 1 - u, 0);
+                nb[u] = a.nout[t];
+                vb[u] = a.valid[(size_t)t * a.Pout + vbase];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (tw > 0 && !found) {
+                    --tw;
+                    const int m = min(min(max(nb[u], 0), a.Pout), n0);
+                    if (k < m && (was_init || tw > 0)) {
+                        if (need > 0) --need;
+                        else if ((vb[u] >> c) & 1u) found = true;
+                    }
+                }
+            }
+        }
+        if (!found) {  // out of history: from frame 0 of the batch and the state the last batch left
+            tw = 0;
+            const double* st = a.state + 2 + (size_t)tid * 12;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                xp[i] = st[i];
+                y[i] = st[4 + i];
+                yd[i] = st[8 + i];
+            }
+        }
+        walk(tw, t_begin, BsBool<false>{});
+    }
+    cooperative_groups::this_grid().sync();
+    if (!active) return;
+    walk(t_begin, t_end, BsBool<true>{});
+    if (chunk == nchunks - 1) {
+        double* st = a.state + 2 + (size_t)tid * 12;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            st[i] = xp[i];
+            st[4 + i] = y[i];
+            st[8 + i] = yd[i];
+        }
+        if (tid == 0 && !was_init) {
+            a.state[1] = (double)n0;
+            a.state[0] = 1.0;
+        }
+    }
+}
+
 // pass B (chunk 0 carries M = 0 and b = its true end state, so the chain start_(c+1) = M_c start_c + b_c holds for
 // every chunk from an arbitrary start_0): see blender_smooth_carry_scan_kernel below.
 
@@ -691,6 +836,7 @@ extern "C" int snowtri_blender_smooth_destroy(snowtri_blender_smooth_t* s) {
 extern "C" int snowtri_blender_smooth_set_chunked(snowtri_blender_smooth_t* s, int enabled) {
     if (!s) return SNOWTRI_E_ARG;
     s->sequential = enabled ? 0 : 1;
+    s->force_scan = enabled == 2 ? 1 : 0;
     return SNOWTRI_OK;
 }
 
@@ -723,6 +869,62 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
     }
     const int threads = s->P * SNOWTRI_NCTRL;
     cudaStream_t st = (cudaStream_t)stream;
+    bool one_pass = false;
+    if (!s->sequential && !s->force_scan && F > 2 * kBsChunk) {
+        if (s->forget_T != delta_time) {   // powers of the state matrix of one present, valid frame (see snowtri_smooth.cu)
+            for (int c = 0; c < SNOWTRI_NCTRL; ++c) {
+                const double T = delta_time, k2 = 1.0 / a.inv_k2[c], g = T / k2;
+                const double A[9] = {0, 0, 0, 0, 1, T, -a.k3[c] / k2, -g, 1 - g * (T + a.k1[c])};
+                double pw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nx[9];
+                s->forget[c] = 0;
+                for (int n = 1; n <= kBsMaxForget && !s->forget[c]; ++n) {
+                    double big = 0;
+                    for (int r_ = 0; r_ < 3; ++r_)
+                        for (int c_ = 0; c_ < 3; ++c_) {
+                            double v = 0;
+                            for (int m_ = 0; m_ < 3; ++m_) v += A[r_ * 3 + m_] * pw[m_ * 3 + c_];
+                            nx[r_ * 3 + c_] = v;
+                            big = fmax(big, fabs(v));
+                        }
+                    memcpy(pw, nx, sizeof(pw));
+                    if (big != big) break;
+                    if (big < 1e-19) s->forget[c] = n;
+                }
+            }
+            s->forget_T = delta_time;
+        }
+        int wmax = 0;
+        bool all = true;
+        for (int c = 0; c < SNOWTRI_NCTRL; ++c) {
+            all = all && s->forget[c] > 0;
+            wmax = s->forget[c] > wmax ? s->forget[c] : wmax;
+            a.forget[c] = s->forget[c];
+        }
+        if (all && !s->coop_blocks) {
+            int dev_coop = 0, per_sm_f = 0, per_sm_d = 0;
+            CUDA_TRY(h, cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, s->device));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, blender_smooth_overlap_kernel<float4>, 96, 0));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, blender_smooth_overlap_kernel<double4>, 96, 0));
+            const int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
+            s->coop_blocks = dev_coop && per_sm > 0 ? per_sm * h->sm_count : -1;
+        }
+        if (all && s->coop_blocks > 0) {
+            int L = 128;   // frames per chunk
+            if (const char* e = getenv("SNOWTRI_BS_CHUNK")) L = atoi(e) >= 16 ? atoi(e) : L;   // experiments
+            const long long max_threads = (long long)s->coop_blocks * 96;
+            while (((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;
+            int nchunks = (F + L - 1) / L;
+            const long long g2 = ((long long)nchunks * threads + 95) / 96;
+            if (g2 <= s->coop_blocks) {
+                void* args[] = {(void*)&a, (void*)&L, (void*)&nchunks};
+                const void* fn = f64 ? (const void*)blender_smooth_overlap_kernel<double4> : (const void*)blender_smooth_overlap_kernel<float4>;
+                CUDA_TRY(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)g2), dim3(96), args, 0, st));
+                h->launches += 1;
+                one_pass = true;
+            }
+        }
+    }
+    if (one_pass) return SNOWTRI_OK;
     if (s->sequential || F <= 2 * kBsChunk) {
         if (f64) blender_smooth_kernel<double4><<<(threads + 95) / 96, 96, 0, st>>>(a);
         else blender_smooth_kernel<float4><<<(threads + 95) / 96, 96, 0, st>>>(a);

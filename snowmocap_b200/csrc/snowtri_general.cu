@@ -189,6 +189,10 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
     const int pb = P <= 4 ? 4 : 8;   // secondary persons scored side by side in the first-generation keep kernel
     const int nchunk = (keypoint_num + 31) / 32;
     const int tpp = (P + kTile - 1) / kTile;
+    // frames with at most this many candidates are clustered by one warp (no CTA barriers in the greedy chain), larger
+    // ones by one CTA: BASELINE configs[2] (448 candidates) 0.126 -> 0.089 ms per 10 000 frames (profiles/r3d)
+    int cluster_warp_max = 512;
+    if (const char* e5 = getenv("SNOWTRI_CLUSTER_WARP_MAX")) cluster_warp_max = atoi(e5);   // experiments
     int last_grid = 0;
     for (int f0 = 0; f0 < F; f0 += (int)fc_max) {
         const int fc = F - f0 < fc_max ? F - f0 : (int)fc_max;
@@ -273,7 +277,7 @@ static int general_run(snowtri_t* h, const float* d_kpts, const float* d_scores,
         }
         // ---- ordered compaction + greedy clustering (+ member decode and row descriptors for the new fuse)
         if (a.ncand > 16384) gen_cluster_block_kernel<1024><<<fc, 1024, 0, st>>>(a);   // (7 680 candidates: 256 threads 0.43 ms, 1 024 threads 0.68 ms per 2 000 frames; 126 976: 1 024 threads 2.4x faster)
-        else if (a.ncand > 64) gen_cluster_block_kernel<256><<<fc, 256, 0, st>>>(a);
+        else if (a.ncand > cluster_warp_max) gen_cluster_block_kernel<256><<<fc, 256, 0, st>>>(a);
         else gen_cluster_warp_kernel<<<(fc + kGenWarps - 1) / kGenWarps, kGenWarps * 32, 0, st>>>(a);
         h->launches += 1;
         // ---- fuse + person score + persons per frame

@@ -280,17 +280,16 @@ __device__ __forceinline__ void match_decide(const GenArgs& a, const double* cam
 // so a candidate needs two running sums and no per-joint selects (27 -> 23 instructions per evaluation).  What the
 // sums leave out:
 //   * a joint whose gate sits inside its guard band adds at most kappa (sm + ss) to the upper bound, kappa =
-//     r_sure (1 + 2 kDistDelta r_sure): the lane counts such joints (`nband`, all 16 candidates of the tile together)
-//     and the tile's upper bounds all get  kappa * sum over lanes of nband * max(sm + ss)  -- a fraction of a joint's
-//     score, against thresholds of J joint scores;
+//     r_sure (1 + 2 kDistDelta r_sure): the lane adds up sm + ss of such joints (`bandq`, all 16 candidates of the tile
+//     together; scores that pass the keypoint threshold are >= 0 on this path) and the tile's upper bounds all get
+//     kappa * sum over lanes of bandq -- a fraction of a joint's score, against thresholds of J joint scores;
 //   * a joint with t > 1/2 (rays that pass within 0.02 mm) has no upper bound: it sets the candidate's bit in `wild`
 //     (one register per lane for the 16 candidates) and the candidate's upper bound is +inf.
-// The running maximum of sm + ss (`qmax`) is taken over every ray of the pass, counted or not.
 // FULL: all 4 + 4 persons of the tile are present (warp-uniform; the usual case) -- no row selects, no count tests.
 template <bool FULL, bool JM>
 __device__ __forceinline__ void match_eval_sums(const MatchItem& t, int J, int j, bool valid, const MatchGate& g,
                                                 float (&s1)[kTile * kTile], float (&s2)[kTile * kTile], unsigned& wild,
-                                                unsigned& nband, float& qmax) {
+                                                float& bandq) {
     float4 m[kTile], s[kTile];
     float sm[kTile], ss[kTile], lim_sure[kTile], lim_maybe[kTile];
     const float4 *pm = t.rm, *ps = t.rs;
@@ -325,7 +324,6 @@ __device__ __forceinline__ void match_eval_sums(const MatchItem& t, int J, int j
         lim_maybe[k] = oks ? g.r_maybe : INFINITY;
         s[k].w = fabsf(s[k].w);
     }
-    qmax = fmaxf(qmax, fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3])) + fmaxf(fmaxf(ss[0], ss[1]), fmaxf(ss[2], ss[3])));
     constexpr float kTight = 0.5f / kDistDelta;
 #pragma unroll
     for (int i = 0; i < kTile; ++i) {
@@ -343,7 +341,8 @@ __device__ __forceinline__ void match_eval_sums(const MatchItem& t, int J, int j
             const float dn = fmaf(e.x, s[k].x, fmaf(e.y, s[k].y, e.z * s[k].z));
             const float nn = fmaf(m[i].w, s[k].w, -(B * B));   // |hm x hs|^2
             const float rd = fmaf(nn, rsqrt_fast(nn * (dn * dn)), -pen);  // sqrt(n.n)/|d.n| = 1/dist
-            const float w = (sm[i] + ss[k]) * rd;              // score / 0.0005
+            const float q = sm[i] + ss[k];
+            const float w = q * rd;                            // score / 0.0005
             // dist > dthr is gated (strict); a NaN distance is not (Q8/Q9): it passes the tests and poisons the sums.
             //   pass = !(rd < lim_sure);  sure = pass && !(rd > kTight);  wild = pass && rd > kTight;
             //   band = !pass && !(rd < lim_maybe)
@@ -356,9 +355,9 @@ __device__ __forceinline__ void match_eval_sums(const MatchItem& t, int J, int j
                 "@ps add.f32 %0, %0, %8;\n\t"
                 "@ps fma.rn.f32 %1, %8, %4, %1;\n\t"
                 "@pw or.b32 %2, %2, %9;\n\t"
-                "@pb add.u32 %3, %3, 1;\n\t}"
-                : "+f"(s1[i * kTile + k]), "+f"(s2[i * kTile + k]), "+r"(wild), "+r"(nband)
-                : "f"(rd), "f"(lim_sure[k]), "f"(lim_maybe[k]), "f"(kTight), "f"(w), "r"(1u << (i * kTile + k)));
+                "@pb add.f32 %3, %3, %10;\n\t}"
+                : "+f"(s1[i * kTile + k]), "+f"(s2[i * kTile + k]), "+r"(wild), "+f"(bandq)
+                : "f"(rd), "f"(lim_sure[k]), "f"(lim_maybe[k]), "f"(kTight), "f"(w), "r"(1u << (i * kTile + k)), "f"(q));
         }
     }
 }
@@ -393,12 +392,12 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
 #pragma unroll
         for (int i = 0; i < kTile * kTile; ++i) lo[i] = hi[i] = 0.f;
 #if MATCH_SUMS
-        unsigned wild = 0u, nband = 0u;
-        float qmax = 0.f;
+        unsigned wild = 0u;
+        float bandq = 0.f;
         auto passes = [&](auto fullc, auto jmc) {
             for (int j0 = 0; j0 < a.J; j0 += 32) {
                 const bool valid = j0 + lane < a.J;
-                match_eval_sums<decltype(fullc)::value, decltype(jmc)::value>(t, a.J, valid ? j0 + lane : a.J - 1, valid, g, lo, hi, wild, nband, qmax);
+                match_eval_sums<decltype(fullc)::value, decltype(jmc)::value>(t, a.J, valid ? j0 + lane : a.J - 1, valid, g, lo, hi, wild, bandq);
             }
         };
         const bool full = t.nm == kTile && t.ns == kTile;
@@ -408,7 +407,7 @@ __device__ __forceinline__ void gen_match_item(const GenArgs& a, const double* c
         wild = __reduce_or_sync(kFull, wild);
         // guard-band joints of the whole tile, charged to every candidate; 1.001: float32 rounding of this small term
         // (a threshold below 2 kDistDelta puts the band itself beyond t = 1/2: no bound)
-        const float bsum = warp_sum((float)nband * qmax);
+        const float bsum = warp_sum(bandq);
         const float kappa = g.r_sure <= 0.5f / kDistDelta ? g.r_sure * fmaf(2.f * kDistDelta, g.r_sure, 1.f) * 1.001f : INFINITY;
         const float band = bsum > 0.f ? bsum * kappa : 0.f;
         lo_tot = fmaf(-kDistDelta, S2, S1);

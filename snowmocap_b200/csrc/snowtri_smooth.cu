@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
+
 #include "snowtri_internal.h"
 
 struct snowtri_smooth_state {
@@ -41,6 +43,10 @@ struct snowtri_smooth_state {
     size_t work_chunks;
     double apow_T;
     int sequential;   // 1 = always the single-launch sequential kernel
+    int force_scan;   // 1 = long batches always take the chunk scan (pass A / B / C)
+    int coop_blocks;  // CTAs of smooth_overlap_kernel a cooperative launch can hold (0: not asked yet)
+    int forget;       // frames after which the follower's state no longer reaches the output in float64 (0: never within kMaxForget)
+    double forget_T;  // delta_time `forget` was computed for
     double apow_host[(128 + 1) * 9];  // (kChunk + 1) matrices
 };
 
@@ -59,6 +65,11 @@ struct SmoothArgs {
 #define SMOOTH_BATCH_BYTES 256
 #endif
 constexpr int kSmoothBatchBytes = SMOOTH_BATCH_BYTES;  // input bytes a thread holds in registers per batch (16 float4 / 8 double4)  -- measured 128: 0.247 ms, 256: 0.240 ms, 512: 0.265 ms per 131 072 frames
+
+template <bool B>
+struct SBool {
+    static constexpr bool value = B;
+};
 
 template <typename V>  // float4 or double4
 __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
@@ -254,6 +265,129 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
     }
 }
 
+
+// ---- one-pass path: chunks with a warm-up instead of a hand-over ------------------------------------------------
+// The follower is a stable filter: W present frames after ANY start state the state is the same to the last bit of a
+// float64 (|A^W| < 1e-19 for the state matrix A of one present frame; the host finds W from the powers of A -- 79 frames
+// for the reference's f = 2, z = 0.75, r = 0 at 30 fps).  So a (chunk, person, joint) thread does not need the state its
+// predecessor ends with: it starts from a ZERO state W present frames before its chunk, walks those frames without
+// writing, and is exact from its first own frame on.  One launch, the batch is read 1 + W/L times and written once
+// (pass A / B / C: read twice, written once, four launches and a work array).  A thread that runs out of history
+// before it has seen W present frames (first chunk, a person that was absent) starts from the carried state at frame 0 of
+// the batch, i.e. it is the sequential recurrence.
+// The points are smoothed IN PLACE, and a warm-up reads frames that belong to earlier chunks: the launch is cooperative
+// (every CTA resident) and a grid-wide barrier separates the warm-ups -- which read only frames before the thread's own
+// chunk, the carried state and the clip header -- from the chunk walks, which read and write only the thread's own
+// frames, the state after the batch and the header.
+constexpr int kMaxForget = 256;   // slower filters take the chunk scan
+
+template <typename V>
+__global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a, int L, int W, int nchunks) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nthr = a.P * a.J;
+    const bool active = gid < (long long)nchunks * nthr;
+    const int chunk = active ? (int)(gid / nthr) : 0, tid = active ? (int)(gid - (long long)chunk * nthr) : 0;
+    const int k = tid / a.J, j = tid - k * a.J;
+    const int t_begin = chunk * L, t_end = min(a.F, t_begin + L);
+    const bool was_init = a.state[0] != 0.0;
+    const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
+    const size_t N = (size_t)a.P * a.J * 3, ch = ((size_t)k * a.J + j) * 3;
+    double xp[3] = {0, 0, 0}, y[3] = {0, 0, 0}, yd[3] = {0, 0, 0};
+    V* pts = reinterpret_cast<V*>(a.pts);
+    const size_t stride = (size_t)a.Pout * a.J;
+    const bool inrange = k < a.Pout;
+    const size_t base = (size_t)(inrange ? k : 0) * a.J + j;
+    constexpr int NB = kSmoothBatchBytes / (int)sizeof(V);
+    // frames [t_from, t_to) in order, inputs a batch at a time (see smooth_chunk_kernel); OWN: the thread's own frames
+    auto walk = [&](int t_from, int t_to, auto ownc) {
+        constexpr bool OWN = decltype(ownc)::value;
+        for (int t0 = t_from; t0 < t_to; t0 += NB) {
+            V buf[NB];
+            int nb[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int t = min(t0 + u, t_to - 1);
+                buf[u] = pts[(size_t)t * stride + base];
+                nb[u] = a.nout[t];
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                const int t = t0 + u;
+                if (t >= t_to) break;
+                const V p = buf[u];
+                const int n = min(max(nb[u], 0), a.Pout);
+                const double x[3] = {(double)p.x, (double)p.y, (double)p.z};
+                if (!was_init && t == 0) {  // first frame of the clip: seed, pass through (reference :177-184)
+                    if (k < n0) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            xp[c] = y[c] = x[c];
+                            yd[c] = 0.0;
+                        }
+                    }
+                    if (OWN && tid == 0) a.nsm[t] = n;
+                    continue;
+                }
+                const int m = min(n, n0);
+                if (OWN && tid == 0) a.nsm[t] = m;
+                if (k < m) {
+                    follower_step(a, x, xp, y, yd);
+                    if (OWN) {
+                        V o = p;
+                        o.x = (decltype(o.x))y[0];
+                        o.y = (decltype(o.y))y[1];
+                        o.z = (decltype(o.z))y[2];
+                        pts[(size_t)t * stride + base] = o;
+                    }
+                }
+            }
+        }
+    };
+    if (active) {
+        // warm-up start: W present frames of this person before the chunk (the seed frame of a clip is not a step)
+        // (person counts fetched eight frames at a time: one by one this walk is ~W dependent L2 round trips)
+        int tw = t_begin, need = W;
+        while (tw > 0 && need > 0) {
+            int nb[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) nb[u] = a.nout[max(tw - 1 - u, 0)];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (tw > 0 && need > 0) {
+                    --tw;
+                    const int m = min(min(max(nb[u], 0), a.Pout), n0);
+                    if (k < m && (was_init || tw > 0)) --need;
+                }
+            }
+        }
+        if (need > 0) {  // out of history: the walk starts at frame 0 of the batch, from the state the last batch left
+            tw = 0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                xp[c] = a.state[2 + ch + c];
+                y[c] = a.state[2 + N + ch + c];
+                yd[c] = a.state[2 + 2 * N + ch + c];
+            }
+        }
+        walk(tw, t_begin, SBool<false>{});
+    }
+    cooperative_groups::this_grid().sync();
+    if (!active) return;
+    walk(t_begin, t_end, SBool<true>{});
+    if (chunk == nchunks - 1) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a.state[2 + ch + c] = xp[c];
+            a.state[2 + N + ch + c] = y[c];
+            a.state[2 + 2 * N + ch + c] = yd[c];
+        }
+        if (tid == 0 && !was_init) {
+            a.state[1] = (double)n0;
+            a.state[0] = 1.0;
+        }
+    }
+}
+
 // Pass B, one launch: the chunk maps of a (person, joint, axis) channel are affine, so their hand-over is a prefix
 // scan under composition.  One CTA per channel, a thread per chunk (blocks of kScanThreads chunks, the state carried
 // from block to block): warp-level Hillis-Steele scan by shuffles (5 levels), the 16 warp totals scanned by warp 0,
@@ -439,6 +573,7 @@ extern "C" int snowtri_smooth_destroy(snowtri_smooth_t* s) {
 extern "C" int snowtri_smooth_set_chunked(snowtri_smooth_t* s, int enabled) {
     if (!s) return SNOWTRI_E_ARG;
     s->sequential = enabled ? 0 : 1;
+    s->force_scan = enabled == 2 ? 1 : 0;
     return SNOWTRI_OK;
 }
 
@@ -477,6 +612,57 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
         CUDA_TRY(h, cudaGetLastError());
         h->launches += 2;
         return SNOWTRI_OK;
+    }
+    // state matrix of one present frame, (xp, y, yd)' = A (xp, y, yd) + b x; its powers say after how many frames the
+    // follower has forgotten its start state (smooth_overlap_kernel) and feed the chunk scan
+    if (s->forget_T != delta_time) {
+        const double T = delta_time, g = T / k2;
+        const double A[9] = {0, 0, 0, 0, 1, T, -a.k3 / k2, -g, 1 - g * (T + a.k1)};
+        double pw[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, nx[9];
+        s->forget = 0;
+        for (int n = 1; n <= kMaxForget && !s->forget; ++n) {
+            double big = 0;
+            for (int r_ = 0; r_ < 3; ++r_)
+                for (int c_ = 0; c_ < 3; ++c_) {
+                    double v = 0;
+                    for (int m_ = 0; m_ < 3; ++m_) v += A[r_ * 3 + m_] * pw[m_ * 3 + c_];
+                    nx[r_ * 3 + c_] = v;
+                    big = fmax(big, fabs(v));
+                }
+            memcpy(pw, nx, sizeof(pw));
+            if (big != big) break;            // absurd parameters: never
+            if (big < 1e-19) s->forget = n;
+        }
+        s->forget_T = delta_time;
+    }
+    if (s->forget > 0 && !s->force_scan) {
+        // one-pass path: a cooperative launch, so the chunk length is what lets every CTA be resident
+        if (!s->coop_blocks) {
+            int dev_coop = 0, per_sm_f = 0, per_sm_d = 0, sms = 0;
+            CUDA_TRY(h, cudaDeviceGetAttribute(&dev_coop, cudaDevAttrCooperativeLaunch, s->device));
+            CUDA_TRY(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_f, smooth_overlap_kernel<float4>, 128, 0));
+            CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_d, smooth_overlap_kernel<double4>, 128, 0));
+            const int per_sm = per_sm_f < per_sm_d ? per_sm_f : per_sm_d;
+            s->coop_blocks = dev_coop && per_sm > 0 ? per_sm * sms : -1;
+        }
+        if (s->coop_blocks > 0) {
+            int L = 256;   // frames per chunk: the batch is read 1 + forget/L times; shorter chunks = more threads in flight (131 072 frames x 133 joints: 256 or 320 frames 0.140 ms, 384 0.153, 512 0.168, 1024 0.232; profiles/r3e)
+            if (const char* e = getenv("SNOWTRI_SMOOTH_CHUNK")) L = atoi(e) >= 32 ? atoi(e) : L;   // experiments
+            while (L < 2 * s->forget) L *= 2;
+            const long long max_threads = (long long)s->coop_blocks * 128;
+            while (((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;   // (one chunk always fits or the test below fails)
+            int nchunks = (F + L - 1) / L;
+            const long long g2 = ((long long)nchunks * threads + 127) / 128;
+            if (g2 <= s->coop_blocks) {
+                int W = s->forget;
+                void* args[] = {(void*)&a, (void*)&L, (void*)&W, (void*)&nchunks};
+                const void* fn = f64 ? (const void*)smooth_overlap_kernel<double4> : (const void*)smooth_overlap_kernel<float4>;
+                CUDA_TRY(h, cudaLaunchCooperativeKernel(fn, dim3((unsigned)g2), dim3(128), args, 0, st));
+                h->launches += 1;
+                return SNOWTRI_OK;
+            }
+        }
     }
     // chunk-parallel path
     const int nchunks = (F + kChunk - 1) / kChunk;

@@ -276,8 +276,10 @@ class SmoothState:
                                                        float(f), float(z), float(r)), engine._h)
 
     def set_chunked(self, enabled=True):
-        """Long batches run as parallel 128-frame chunks (default); False forces the sequential kernel."""
-        _lib.check(self._lib.snowtri_smooth_set_chunked(self._s, 1 if enabled else 0), self._eng._h)
+        """Long batches run as parallel chunks (default: one pass with a warm-up per chunk when the filter forgets its
+        state within 256 frames, else the chunk scan); ``"scan"`` forces the chunk scan, False the sequential kernel."""
+        mode = 2 if enabled == "scan" else (1 if enabled else 0)
+        _lib.check(self._lib.snowtri_smooth_set_chunked(self._s, mode), self._eng._h)
 
     def reset(self):
         """The next frame starts a new clip (passes through and seeds the followers)."""

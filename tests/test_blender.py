@@ -401,10 +401,12 @@ def test_batch_clip_matches_reference_golden(torch_cuda, dtype, tol, split):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("chunked,batches", [(True, [600]), (False, [600]), (True, [290, 310]), (True, [1, 599]),
-                                             (True, [300, 40, 260]), (True, [9000]), (True, [4500, 4500])])
+                                             (True, [300, 40, 260]), (True, [9000]), (True, [4500, 4500]),
+                                             ("scan", [9000]), ("scan", [300, 40, 260]), ("scan", [4500, 4500])])
 def test_batch_smooth_long_clip_vs_oracle(torch_cuda, chunked, batches):
-    """Person count changing, random invalid control points, non-zero r; the chunk-parallel path (batches of more
-    than 256 frames; 9000 frames = 71 chunks in 3 groups), the sequential kernel, and a clip streamed through both."""
+    """Person count changing, random invalid control points, non-zero r; the chunk-parallel paths (batches of more
+    than 256 frames: one pass with a warm-up per chunk by default, "scan" = the chunk scan, 9000 frames = 71 chunks in
+    3 groups), the sequential kernel, and a clip streamed through them."""
     torch = torch_cuda
     from snowmocap_b200.blender import BlenderSmoothState
     rng = np.random.default_rng(77)

@@ -479,7 +479,7 @@ def test_smooth_float32_layout_long_clip_vs_c_oracle(torch_cuda):
     assert np.array_equal(nsm2, nsm) and torch.equal(out2, out)   # reset starts the same clip again
 
 
-@pytest.mark.parametrize("chunked", [True, False])
+@pytest.mark.parametrize("chunked", [True, False, "scan"])
 @pytest.mark.parametrize("batches", [(3000,), (1, 700, 299, 2000), (300, 2700)])
 def test_smooth_long_clip_float64_vs_c_oracle(torch_cuda, chunked, batches):
     """Chunk-parallel and sequential kernels, whole clip or streamed batches, ragged person count."""

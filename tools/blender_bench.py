@@ -82,7 +82,7 @@ def smooth():
 
 res_s = {}
 if not os.environ.get("BLENDER_BENCH_NO_SMOOTH"):
-    for name, chunked in (("chunked", True), ("sequential", False)):
+    for name, chunked in (("chunked", True), ("scan", "scan"), ("sequential", False)):
         st.set_chunked(chunked)
         ms_s = timed(smooth, steps=5, warm=2)
         res_s[name] = {"ms": ms_s, "frames_per_s": F / (ms_s * 1e-3), "ns_per_frame_step": ms_s * 1e6 / F}
