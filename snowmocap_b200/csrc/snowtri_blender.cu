@@ -909,7 +909,7 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
             s->coop_blocks = dev_coop && per_sm > 0 ? per_sm * h->sm_count : -1;
         }
         if (all && s->coop_blocks > 0) {
-            int L = 128;   // frames per chunk
+            int L = 64;   // frames per chunk (131 072 frames x 24 control points: 32 or 64 frames 0.058 ms, 128 0.061, 256 0.071; profiles/r3g)
             if (const char* e = getenv("SNOWTRI_BS_CHUNK")) L = atoi(e) >= 16 ? atoi(e) : L;   // experiments
             const long long max_threads = (long long)s->coop_blocks * 96;
             while (((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;

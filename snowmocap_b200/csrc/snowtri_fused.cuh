@@ -113,6 +113,82 @@ __device__ __forceinline__ int cluster_warp(int N, const uint32_t* klist, const 
 // wtmp: 2*NW+4 ints of scratch.  Must be called by all NT threads; returns K to every thread.
 // The per-warp counts of a CTA pass (wcnt[NW], NW <= 32): `off` = sum over the warps before `warp`, `tot` = sum over all.
 // Every warp scans the NW counts with its own lanes (5 shuffle steps) instead of every thread walking the array.
+// The same for up to 32 * kClusterRegs kept candidates, from registers: lane l holds candidates l, l + 32, ... (index and
+// centre), the main's centre travels by shuffles, the absorbed flags are a bit mask per lane.  cluster_warp reads
+// klist -> centre from global memory for every main and every block of candidates -- three dependent L2 round trips per
+// block, ~80 us per frame of BASELINE configs[2] (140 kept candidates, 8 mains); here the frame's centres are read once.
+// Same sweeps, same order, same comparisons (centre_far on the same differences): identical clusters.
+constexpr int kClusterRegs = 8;
+__device__ __forceinline__ int cluster_warp_regs(int N, const uint32_t* klist, const double* cen, uint32_t* memb, int* cstart,
+                                                 int* cn, double tol2, int num_tol, int lane) {
+    double cx[kClusterRegs], cy[kClusterRegs], cz[kClusterRegs];
+    uint32_t id[kClusterRegs];
+#pragma unroll
+    for (int r = 0; r < kClusterRegs; ++r) {
+        const int i = r * 32 + lane;
+        id[r] = i < N ? klist[i] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < kClusterRegs; ++r) {
+        const double* c = cen + 3 * (size_t)id[r];
+        const bool in = r * 32 + lane < N;
+        cx[r] = in ? c[0] : 0.0;
+        cy[r] = in ? c[1] : 0.0;
+        cz[r] = in ? c[2] : 0.0;
+    }
+    unsigned absorbed = 0u;  // bit r: candidate r * 32 + lane
+    int K = 0, mpos = 0, mc = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    while (mc < N - 1) {  // the last candidate is never a main (Q1/Q2)
+        const int rm = mc >> 5;
+        double mx = cx[0], my = cy[0], mz = cz[0];
+        uint32_t mid = id[0];
+#pragma unroll
+        for (int r = 1; r < kClusterRegs; ++r)
+            if (r == rm) {
+                mx = cx[r]; my = cy[r]; mz = cz[r];
+                mid = id[r];
+            }
+        mx = __shfl_sync(kFull, mx, mc & 31);
+        my = __shfl_sync(kFull, my, mc & 31);
+        mz = __shfl_sync(kFull, mz, mc & 31);
+        mid = __shfl_sync(kFull, mid, mc & 31);
+        const int start = mpos;
+        if (lane == 0) memb[mpos] = mid;
+        mpos += 1;
+        int next = N;
+#pragma unroll
+        for (int r = 0; r < kClusterRegs; ++r) {
+            const int base = r * 32;
+            if (base + 31 <= mc || base >= N) continue;  // warp-uniform: blocks before the main / beyond the list
+            const int i = base + lane;
+            const bool live = (i > mc) && (i < N) && !((absorbed >> r) & 1u);
+            const bool take = live && !centre_far(mx - cx[r], my - cy[r], mz - cz[r], tol2);  // distance to the MAIN (Q3)
+            const unsigned bt = __ballot_sync(kFull, take);
+            if (take) {
+                memb[mpos + __popc(bt & lt)] = id[r];
+                absorbed |= 1u << r;
+            }
+            mpos += __popc(bt);
+            const unsigned bl = __ballot_sync(kFull, live && !take);
+            if (bl != 0u && next == N) next = base + __ffs(bl) - 1;
+        }
+        const int n = mpos - start;
+        if (n >= num_tol) {
+            if (lane == 0) {
+                cstart[K] = start;
+                cn[K] = n;
+            }
+            ++K;
+        } else {
+            mpos = start;  // members stay absorbed (Q5)
+        }
+        mc = next;
+    }
+    __syncwarp();
+    return K;
+}
+
 template <int NW>
 __device__ __forceinline__ void cluster_warp_prefix(const int* wcnt, int warp, int lane, int& off, int& tot) {
     static_assert(NW <= 32, "one lane per warp of the CTA");

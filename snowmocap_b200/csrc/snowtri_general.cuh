@@ -335,16 +335,29 @@ __global__ void __launch_bounds__(kGenWarps * 32) gen_cluster_warp_kernel(const 
     const unsigned lt = (1u << lane) - 1u;
     uint32_t* kl = a.klist + o;
     int nk = 0;
-    for (int base = 0; base < a.ncand; base += 32) {
-        const int i = base + lane;
-        const bool k = (i < a.ncand) && a.keep[o + i];
-        const unsigned b = __ballot_sync(kFull, k);
-        if (k) kl[nk + __popc(b & lt)] = (uint32_t)i;
-        nk += __popc(b);
+    // ordered compaction of the kept candidates, the keep bytes fetched 16 blocks at a time (one by one every block is
+    // an L2 round trip)
+    for (int base0 = 0; base0 < a.ncand; base0 += 16 * 32) {
+        unsigned char kb[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int i = base0 + u * 32 + lane;
+            kb[u] = i < a.ncand ? a.keep[o + i] : (unsigned char)0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            if (base0 + u * 32 >= a.ncand) break;
+            const bool k = kb[u] != 0;
+            const unsigned b = __ballot_sync(kFull, k);
+            if (k) kl[nk + __popc(b & lt)] = (uint32_t)(base0 + u * 32 + lane);
+            nk += __popc(b);
+        }
     }
     __syncwarp();
-    const int K = cluster_warp(nk, kl, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o, a.cn + o, a.tol2,
-                               a.prm.num_tol, lane);
+    const int K = nk <= 32 * kClusterRegs
+                      ? cluster_warp_regs(nk, kl, a.cen + 3 * o, a.memb + o, a.cstart + o, a.cn + o, a.tol2, a.prm.num_tol, lane)
+                      : cluster_warp(nk, kl, a.cen + 3 * o, a.ab + o, a.memb + o, a.cstart + o, a.cn + o, a.tol2,
+                                     a.prm.num_tol, lane);
     if (lane == 0) a.kcount[f] = K;
     if (a.tile_counter && f == 0 && lane == 0) *a.tile_counter = 0;
     if (a.memb2) {
