@@ -506,8 +506,59 @@ def time_downstream(torch, eng, out, pout, J, reps=5):
            "snowtri_smooth_run_frac_of_hbm_peak": rows * J * 32 / (t_s * 1e-3) / 1e9 / peak,
            "snowtri_blender_run_frac_of_hbm_peak": rows * 724 / (t_b * 1e-3) / 1e9 / peak,
            "snowtri_blender_smooth_run_frac_of_hbm_peak": rows * 24 * 32 / (t_bs * 1e-3) / 1e9 / peak}
+    res["total_ms"] = t_s + t_b + t_bs
     sm.close()
     bs.close()
+    return res
+
+
+def downstream_cpu_baseline(pout, J, seconds=3.0):
+    """CPU legs of the downstream stages on this box's host cores, one core each (the reference calls them once per
+    frame from a single thread), on bounded samples: the real reference's Human_Triangulation_Smooth when the vendored
+    copy is present (else the C restatement), and the NumPy restatement of Human_Triangulation_To_Blender's control
+    points.  Test infrastructure timed as a baseline, never on the product path."""
+    res = {}
+    rng = np.random.default_rng(3)
+    try:
+        from oracle import ref_runner
+        if ref_runner.available():
+            ref = ref_runner.load()
+            n, prev, t0 = 0, None, time.perf_counter()
+            pts = rng.uniform(-1, 1, (64, pout, J, 3))
+            while time.perf_counter() - t0 < seconds:
+                frame = {"hrnet_triangulate_points": [pts[n % 64, k] for k in range(pout)],
+                         "hrnet_triangulate_keypoint_scores": [np.ones(J)] * pout, "hrnet_triangulate_person_scores": [1.0] * pout}
+                prev = ref.Human_Triangulation_Smooth(frame, prev, 2.5, 0.75, 0.0, 1 / 30)
+                n += 1
+            dt = time.perf_counter() - t0
+            res["Human_Triangulation_Smooth"] = {"value": n * pout * J / dt, "unit": "keypoints/s", "cores": 1, "kind": "reference",
+                                                 "sample": f"{n} frames x {pout} person(s) x {J} joints in {dt:.1f} s, the real reference frame by frame"}
+    except Exception as e:
+        res["Human_Triangulation_Smooth"] = {"error": str(e)[:160]}
+    try:
+        from oracle import c_oracle
+        Fc = 20000
+        pts = rng.uniform(-1, 1, (Fc, pout, J, 3))
+        t0 = time.perf_counter()
+        c_oracle.smooth(pts, np.full(Fc, pout, np.int32), 2.5, 0.75, 0.0, 1 / 30)
+        dt = time.perf_counter() - t0
+        res["smooth_c_port"] = {"value": Fc * pout * J / dt, "unit": "keypoints/s", "cores": 1, "kind": "port",
+                                "sample": f"{Fc} frames in {dt:.2f} s, C restatement (oracle/snow_oracle.c)"}
+    except Exception as e:
+        res["smooth_c_port"] = {"error": str(e)[:160]}
+    try:
+        from oracle import blender_oracle as bo
+        rows = (rng.random((256, 133, 3)) * 2.0).astype(np.float32).astype(np.float64)
+        n, t0 = 0, time.perf_counter()
+        with np.errstate(all="ignore"):
+            while time.perf_counter() - t0 < seconds:
+                bo.control_points(rows[n % 256])
+                n += 1
+        dt = time.perf_counter() - t0
+        res["blender_control_points"] = {"value": n / dt, "unit": "persons/s", "cores": 1, "kind": "port",
+                                         "sample": f"{n} person rows in {dt:.1f} s, NumPy restatement of blender.py:93-143"}
+    except Exception as e:
+        res["blender_control_points"] = {"error": str(e)[:160]}
     return res
 
 
@@ -834,6 +885,8 @@ def main():
     if rank == 0 and world == 1 and J >= 130 and not args.no_others:
         try:
             downstream = time_downstream(torch, eng, out, pout, J)
+            if not args.no_cpu:
+                downstream["cpu_baseline"] = downstream_cpu_baseline(pout, J)
         except Exception as e:   # reported, not fatal
             downstream = {"error": str(e)[:200]}
 

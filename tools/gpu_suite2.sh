@@ -2,7 +2,7 @@
 # Round-2 GPU-box suite: parity tests, smoke, the default bench line (both arms), launch lists of the timed regions and
 # full ncu captures of the dominant kernels (single-person kernel in both float modes; matching and fuse kernels of cfg3).
 # Usage (from the repo root, through gpurun): bash tools/gpu_suite2.sh [tag]
-tag=${1:-r2z}
+tag=${1:-r3z}
 out=gpurun_out/$tag
 mkdir -p $out
 nvidia-smi > $out/nvidia-smi.txt 2>&1
@@ -20,10 +20,15 @@ for prec in f32 mixed; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:p1_jit -s 4 -c 1 -f -o $out/p1_jit_cfg2_$prec \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e --no-others --no-secondary --precision $prec > $out/ncu_full_cfg2_$prec.log 2>&1
 done
-for k in gen_match_smem_kernel gen_cluster_block_kernel mfuse_kernel; do
+for k in gen_match_smem_kernel gen_cluster_warp_kernel mfuse_kernel; do
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $out/${k}_cfg3_mixed \
     python bench.py --workload cfg3 --steps 2 --warmup 3 --no-cpu --no-e2e --no-others --no-secondary > $out/ncu_full_cfg3_$k.log 2>&1
 done
+for k in smooth_overlap_kernel; do
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $out/${k}_f32 \
+    python tools/smooth_bench.py > $out/ncu_full_$k.log 2>&1
+done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches_smooth.csv python tools/smooth_bench.py > /dev/null 2>&1
 timeout 120 python tools/smooth_bench.py > $out/smooth_bench.json 2> $out/smooth_bench.err
 timeout 300 python tools/blender_bench.py > $out/blender_bench.json 2> $out/blender_bench.err
 tail -3 $out/pytest_gpu.log; tail -4 $out/smoke.log; cut -c1-600 $out/bench_default.json; echo; cut -c1-400 $out/bench_reference.json
