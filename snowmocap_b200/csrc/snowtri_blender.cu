@@ -358,13 +358,26 @@ struct BsChunkArgs {
     int nchunks, NT;
 };
 
-__device__ __forceinline__ void bs_step(const BlenderSmoothArgs& a, double k1, double inv_k2, double k3, bool ok,
-                                        double x, double& xp, double& y, double& yd) {
+// (bulk kernels: the update with its constants folded, 5 instead of 7 float64 operations per channel -- see follower_step
+// in snowtri_smooth.cu; the sequential kernel keeps the reference's operation order)
+struct BsCoef {
+    double T, g, cd, cx, cp;
+};
+__device__ __forceinline__ BsCoef bs_coef(const BlenderSmoothArgs& a, double k1, double inv_k2, double k3) {
+    BsCoef q;
+    q.T = a.T;
+    q.g = a.T * inv_k2;
+    q.cd = 1.0 - q.g * k1;
+    q.cx = q.g * (1.0 + k3 * a.invT);
+    q.cp = q.g * (k3 * a.invT);
+    return q;
+}
+__device__ __forceinline__ void bs_step(const BsCoef& q, bool ok, double x, double& xp, double& y, double& yd) {
     const double xi = ok ? x : xp;   // blender.py:157-160
-    const double xd = (xi - xp) * a.invT;   // triangulation.py:15-22
+    const double t1 = fma(q.cx, xi, -(q.cp * xp));   // triangulation.py:15-22
     xp = xi;
-    y = y + a.T * yd;
-    yd = yd + a.T * (xi + k3 * xd - y - k1 * yd) * inv_k2;
+    y = fma(q.T, yd, y);
+    yd = fma(-q.g, y, fma(q.cd, yd, t1));
 }
 
 template <typename V, int PASS>   // PASS 0 = A, 2 = C
@@ -377,6 +390,7 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
     const bool was_init = a.state[0] != 0.0;
     const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
     const double k1 = a.k1[c], inv_k2 = a.inv_k2[c], k3 = a.k3[c];
+    const BsCoef coef = bs_coef(a, k1, inv_k2, k3);
     V* ctrl = reinterpret_cast<V*>(a.ctrl);
     const bool inrange = k < a.Pout;
     const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
@@ -444,7 +458,7 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
             if (PASS == 0 && tid == 0) a.nsm[t] = m;
             if (k < m) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) bs_step(a, k1, inv_k2, k3, ok, x[i], xp[i], y[i], yd[i]);
+                for (int i = 0; i < 4; ++i) bs_step(coef, ok, x[i], xp[i], y[i], yd[i]);
                 if (real) {
                     V o;
                     o.x = (decltype(o.x))y[0];
@@ -454,7 +468,7 @@ __global__ void __launch_bounds__(96) blender_smooth_chunk_kernel(const BsChunkA
                     ctrl[(size_t)t * stride + base] = o;
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 3; ++j) bs_step(a, k1, inv_k2, k3, ok, 0.0, bx[j], by[j], bd[j]);
+                    for (int j = 0; j < 3; ++j) bs_step(coef, ok, 0.0, bx[j], by[j], bd[j]);
                 }
             }
         }
@@ -502,6 +516,7 @@ __global__ void __launch_bounds__(96) blender_smooth_overlap_kernel(const Blende
     const bool was_init = a.state[0] != 0.0;
     const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
     const double k1 = a.k1[c], inv_k2 = a.inv_k2[c], k3 = a.k3[c];
+    const BsCoef coef = bs_coef(a, k1, inv_k2, k3);
     V* ctrl = reinterpret_cast<V*>(a.ctrl);
     const bool inrange = k < a.Pout;
     const size_t stride = (size_t)a.Pout * SNOWTRI_NCTRL;
@@ -546,7 +561,7 @@ __global__ void __launch_bounds__(96) blender_smooth_overlap_kernel(const Blende
                 if (OWN && tid == 0) a.nsm[t] = m;
                 if (k < m) {
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) bs_step(a, k1, inv_k2, k3, ok, x[i], xp[i], y[i], yd[i]);
+                    for (int i = 0; i < 4; ++i) bs_step(coef, ok, x[i], xp[i], y[i], yd[i]);
                     if (OWN) {
                         V o;
                         o.x = (decltype(o.x))y[0];

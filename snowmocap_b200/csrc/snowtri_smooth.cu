@@ -157,15 +157,33 @@ __global__ void __launch_bounds__(128) smooth_kernel(const SmoothArgs a) {
 
 constexpr int kChunk = 128;  // frames per chunk of the parallel path
 
-// One frame of one (person, joint): the reference's update (triangulation.py:15-22) on the three axes.
-__device__ __forceinline__ void follower_step(const SmoothArgs& a, const double* x, double* xp, double* y, double* yd) {
+// One frame of one (person, joint): the reference's update (triangulation.py:15-22) on the three axes, in the bulk
+// kernels with the constants folded:  y' = y + T yd;  yd' = cd yd + cx x - cp xp - g y'  with g = T/k2, cd = 1 - g k1,
+// cx = g (1 + k3/T), cp = g k3/T -- 5 instead of 7 float64 operations per axis and a carried chain of two (the chunk
+// scan of the control points 0.116 -> 0.104 ms; the one-pass kernels are bound by DRAM and did not move).  Same
+// algebra, different rounding (~1e-16 per step, damped by the filter); the sequential kernel of the per-frame drop-in
+// keeps the reference's operation order.
+struct FollowerCoef {
+    double T, g, cd, cx, cp;
+};
+__device__ __forceinline__ FollowerCoef follower_coef(double T, double invT, double k1, double inv_k2, double k3) {
+    FollowerCoef q;
+    q.T = T;
+    q.g = T * inv_k2;
+    q.cd = 1.0 - q.g * k1;
+    q.cx = q.g * (1.0 + k3 * invT);
+    q.cp = q.g * (k3 * invT);
+    return q;
+}
+__device__ __forceinline__ void follower_step1(const FollowerCoef& q, double x, double& xp, double& y, double& yd) {
+    const double t1 = fma(q.cx, x, -(q.cp * xp));
+    xp = x;
+    y = fma(q.T, yd, y);
+    yd = fma(-q.g, y, fma(q.cd, yd, t1));
+}
+__device__ __forceinline__ void follower_step(const FollowerCoef& q, const double* x, double* xp, double* y, double* yd) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const double xd = (x[c] - xp[c]) * a.invT;
-        xp[c] = x[c];
-        y[c] = y[c] + a.T * yd[c];
-        yd[c] = yd[c] + a.T * (x[c] + a.k3 * xd - y[c] - a.k1 * yd[c]) * a.inv_k2;
-    }
+    for (int c = 0; c < 3; ++c) follower_step1(q, x[c], xp[c], y[c], yd[c]);
 }
 
 struct ChunkArgs {
@@ -187,6 +205,7 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
     const int chunk = (int)(gid / nthr), tid = (int)(gid - (long long)chunk * nthr);
     const int k = tid / a.J, j = tid - k * a.J;
     const int t_begin = chunk * kChunk, t_end = min(a.F, t_begin + kChunk);
+    const FollowerCoef coef = follower_coef(a.T, a.invT, a.k1, a.inv_k2, a.k3);
     const bool was_init = a.state[0] != 0.0;
     const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
     const size_t ch = (size_t)k * a.J + j, nch = (size_t)a.P * a.J;
@@ -241,7 +260,7 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
             const int m = min(n, n0);
             if (PASS == 2 && tid == 0) a.nsm[t] = m;
             if (k < m) {
-                follower_step(a, x, xp, y, yd);
+                follower_step(coef, x, xp, y, yd);
                 ++present;
                 if (PASS == 2) {
                     V o = p;
@@ -289,6 +308,7 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
     const int chunk = active ? (int)(gid / nthr) : 0, tid = active ? (int)(gid - (long long)chunk * nthr) : 0;
     const int k = tid / a.J, j = tid - k * a.J;
     const int t_begin = chunk * L, t_end = min(a.F, t_begin + L);
+    const FollowerCoef coef = follower_coef(a.T, a.invT, a.k1, a.inv_k2, a.k3);
     const bool was_init = a.state[0] != 0.0;
     const int n0 = was_init ? (int)a.state[1] : min(min(max(a.nout[0], 0), a.Pout), a.P);
     const size_t N = (size_t)a.P * a.J * 3, ch = ((size_t)k * a.J + j) * 3;
@@ -298,20 +318,27 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
     const bool inrange = k < a.Pout;
     const size_t base = (size_t)(inrange ? k : 0) * a.J + j;
     constexpr int NB = kSmoothBatchBytes / (int)sizeof(V);
-    // frames [t_from, t_to) in order, inputs a batch at a time (see smooth_chunk_kernel); OWN: the thread's own frames
+    // frames [t_from, t_to) in order; OWN: the thread's own frames.  Inputs travel in two half-batches: the loads of the
+    // next half are issued before the steps of the current one, so a thread always has loads in flight.  (Measured
+    // against one batch of 16 per thread: 0.139 vs 0.140 ms at 256-frame chunks, 0.172 vs 0.168 at 512 -- no gain; nor
+    // from 15 instead of 21 float64 operations per step.  At 256-frame chunks the kernel moves 645 MB in 130 us, 76 % of
+    // the measured copy bandwidth with reads and writes of 512-byte pieces interleaved; profiles/r3h, r3i.)
     auto walk = [&](int t_from, int t_to, auto ownc) {
         constexpr bool OWN = decltype(ownc)::value;
-        for (int t0 = t_from; t0 < t_to; t0 += NB) {
-            V buf[NB];
-            int nb[NB];
+        constexpr int NH = NB / 2;
+        V bufA[NH], bufB[NH];
+        int nbA[NH], nbB[NH];
+        auto fetch = [&](V (&buf)[NH], int (&nb)[NH], int t0) {
 #pragma unroll
-            for (int u = 0; u < NB; ++u) {
+            for (int u = 0; u < NH; ++u) {
                 const int t = min(t0 + u, t_to - 1);
                 buf[u] = pts[(size_t)t * stride + base];
                 nb[u] = a.nout[t];
             }
+        };
+        auto steps = [&](const V (&buf)[NH], const int (&nb)[NH], int t0) {
 #pragma unroll
-            for (int u = 0; u < NB; ++u) {
+            for (int u = 0; u < NH; ++u) {
                 const int t = t0 + u;
                 if (t >= t_to) break;
                 const V p = buf[u];
@@ -331,7 +358,7 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
                 const int m = min(n, n0);
                 if (OWN && tid == 0) a.nsm[t] = m;
                 if (k < m) {
-                    follower_step(a, x, xp, y, yd);
+                    follower_step(coef, x, xp, y, yd);
                     if (OWN) {
                         V o = p;
                         o.x = (decltype(o.x))y[0];
@@ -341,6 +368,14 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
                     }
                 }
             }
+        };
+        if (t_from >= t_to) return;
+        fetch(bufA, nbA, t_from);
+        for (int t0 = t_from; t0 < t_to; t0 += 2 * NH) {
+            if (t0 + NH < t_to) fetch(bufB, nbB, t0 + NH);
+            steps(bufA, nbA, t0);
+            if (t0 + 2 * NH < t_to) fetch(bufA, nbA, t0 + 2 * NH);
+            if (t0 + NH < t_to) steps(bufB, nbB, t0 + NH);
         }
     };
     if (active) {

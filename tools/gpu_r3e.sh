@@ -3,7 +3,7 @@
 tag=${1:-r3e}; out=gpurun_out/$tag; mkdir -p $out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_zz_clip.py -m gpu -x -q -k "smooth or clip or pipeline" > $out/pytest_smooth.log 2>&1; echo "pytest rc=$?" >> $out/pytest_smooth.log
 tail -5 $out/pytest_smooth.log
-for L in 160 256 384 512; do
+for L in 256 384 512 1024; do
   echo "chunk $L: $(SNOWTRI_SMOOTH_CHUNK=$L python tools/smooth_bench.py 2>&1 | tail -1 | cut -c1-160)"
 done
 python tools/smooth_bench.py > $out/smooth_bench.json
