@@ -322,7 +322,9 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
     // next half are issued before the steps of the current one, so a thread always has loads in flight.  (Measured
     // against one batch of 16 per thread: 0.139 vs 0.140 ms at 256-frame chunks, 0.172 vs 0.168 at 512 -- no gain; nor
     // from 15 instead of 21 float64 operations per step.  At 256-frame chunks the kernel moves 645 MB in 130 us, 76 % of
-    // the measured copy bandwidth with reads and writes of 512-byte pieces interleaved; profiles/r3h, r3i.)
+    // the measured copy bandwidth with reads and writes of 512-byte pieces interleaved; profiles/r3h, r3i.  Also tried:
+    // the next half staged in shared memory by cp.async, which holds no scoreboard -- 0.167 ms at 256-frame chunks,
+    // 0.164 at 512: slower, profiles/r3j.)
     auto walk = [&](int t_from, int t_to, auto ownc) {
         constexpr bool OWN = decltype(ownc)::value;
         constexpr int NH = NB / 2;

@@ -3,7 +3,7 @@
 tag=${1:-r3i}; out=gpurun_out/$tag; mkdir -p $out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_blender.py tests/test_zz_clip.py -m gpu -x -q -k "smooth or clip or pipeline or blender or Blender" > $out/pytest_smooth.log 2>&1; echo "pytest rc=$?" >> $out/pytest_smooth.log
 tail -4 $out/pytest_smooth.log
-for L in 256 384 512 768; do
+for L in 160 192 256 384 512; do
   echo "chunk $L: $(SNOWTRI_SMOOTH_CHUNK=$L python tools/smooth_bench.py 2>&1 | tail -1 | cut -c1-100)"
 done
 python tools/smooth_bench.py > $out/smooth_bench.json
