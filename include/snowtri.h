@@ -148,8 +148,8 @@ int snowtri_skew_ray(snowtri_t* h, int n, const double* d_hm, const double* d_hs
  *              absent persons are not advanced.  Slots >= d_nsmooth[f] are left untouched.
  * Batches of up to 256 frames run in one launch with a sequential frame loop (the recurrence is sequential);
  * longer batches are cut into chunks that run in parallel.  When the follower forgets its state within 256 present
- * frames to the last bit of a float64 (the powers of its update matrix fall below 1e-19: 79 frames for the reference's
- * f = 2, z = 0.75, r = 0 at 30 fps) every chunk warms up on the frames before it instead of waiting for its
+ * frames to the last bit of a float64 (the powers of its update matrix fall below 1e-19: 80 frames for the reference's
+ * shipped f = 2.5, z = 0.75, r = 0 at 30 fps) every chunk warms up on the frames before it instead of waiting for its
  * predecessor's state: one cooperative launch, the batch read about 1.2 times and written once.  Slower filters take
  * 128-frame chunks with the state handed from chunk to chunk through powers of the (affine) update matrix (a prefix
  * scan of the chunk maps).  snowtri_smooth_set_chunked(s, 0) forces the sequential kernel, (s, 2) the chunk scan,

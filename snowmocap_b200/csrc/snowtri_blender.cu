@@ -578,6 +578,8 @@ __global__ void __launch_bounds__(96) blender_smooth_overlap_kernel(const Blende
         // warm-up start: walking back, W present frames, then the next present frame whose control point is valid
         int tw = t_begin, need = a.forget[c];
         bool found = false;
+        const bool idle = k >= min(n0, a.Pout);   // a follower this batch never advances: its state is carried over
+        if (idle) tw = 0;
         while (tw > 0 && !found) {
             int nb[8];
             unsigned vb[8];
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(96) blender_smooth_overlap_kernel(const Blende
             }
         }
         if (!found) {  // out of history: from frame 0 of the batch and the state the last batch left
-            tw = 0;
+            tw = idle ? t_begin : 0;
             const double* st = a.state + 2 + (size_t)tid * 12;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -927,7 +929,7 @@ static int blender_smooth_run(snowtri_t* h, snowtri_blender_smooth_t* s, void* d
             int L = 64;   // frames per chunk (131 072 frames x 24 control points: 32 or 64 frames 0.058 ms, 128 0.061, 256 0.071; profiles/r3g)
             if (const char* e = getenv("SNOWTRI_BS_CHUNK")) L = atoi(e) >= 16 ? atoi(e) : L;   // experiments
             const long long max_threads = (long long)s->coop_blocks * 96;
-            while (((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;
+            while (L < F && ((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;   // (if even one chunk does not fit, the test below fails)
             int nchunks = (F + L - 1) / L;
             const long long g2 = ((long long)nchunks * threads + 95) / 96;
             if (g2 <= s->coop_blocks) {

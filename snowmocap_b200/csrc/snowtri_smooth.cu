@@ -287,8 +287,8 @@ __global__ void __launch_bounds__(128) smooth_chunk_kernel(const ChunkArgs ca) {
 
 // ---- one-pass path: chunks with a warm-up instead of a hand-over ------------------------------------------------
 // The follower is a stable filter: W present frames after ANY start state the state is the same to the last bit of a
-// float64 (|A^W| < 1e-19 for the state matrix A of one present frame; the host finds W from the powers of A -- 79 frames
-// for the reference's f = 2, z = 0.75, r = 0 at 30 fps).  So a (chunk, person, joint) thread does not need the state its
+// float64 (|A^W| < 1e-19 for the state matrix A of one present frame; the host finds W from the powers of A -- 80 frames
+// for the reference's shipped f = 2.5, z = 0.75, r = 0 at 30 fps).  So a (chunk, person, joint) thread does not need the state its
 // predecessor ends with: it starts from a ZERO state W present frames before its chunk, walks those frames without
 // writing, and is exact from its first own frame on.  One launch, the batch is read 1 + W/L times and written once
 // (pass A / B / C: read twice, written once, four launches and a work array).  A thread that runs out of history
@@ -384,6 +384,7 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
         // warm-up start: W present frames of this person before the chunk (the seed frame of a clip is not a step)
         // (person counts fetched eight frames at a time: one by one this walk is ~W dependent L2 round trips)
         int tw = t_begin, need = W;
+        if (k >= min(n0, a.Pout)) tw = 0;   // a follower this batch never advances: no history to look for, its state is carried over
         while (tw > 0 && need > 0) {
             int nb[8];
 #pragma unroll
@@ -398,7 +399,7 @@ __global__ void __launch_bounds__(128) smooth_overlap_kernel(const SmoothArgs a,
             }
         }
         if (need > 0) {  // out of history: the walk starts at frame 0 of the batch, from the state the last batch left
-            tw = 0;
+            tw = k >= min(n0, a.Pout) ? t_begin : 0;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 xp[c] = a.state[2 + ch + c];
@@ -688,7 +689,7 @@ static int smooth_run(snowtri_t* h, snowtri_smooth_t* s, void* d_pts, bool f64, 
             if (const char* e = getenv("SNOWTRI_SMOOTH_CHUNK")) L = atoi(e) >= 32 ? atoi(e) : L;   // experiments
             while (L < 2 * s->forget) L *= 2;
             const long long max_threads = (long long)s->coop_blocks * 128;
-            while (((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;   // (one chunk always fits or the test below fails)
+            while (L < F && ((long long)(F + L - 1) / L) * threads > max_threads) L *= 2;   // (if even one chunk does not fit, the test below fails)
             int nchunks = (F + L - 1) / L;
             const long long g2 = ((long long)nchunks * threads + 127) / 128;
             if (g2 <= s->coop_blocks) {

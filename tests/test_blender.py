@@ -402,7 +402,9 @@ def test_batch_clip_matches_reference_golden(torch_cuda, dtype, tol, split):
 @pytest.mark.gpu
 @pytest.mark.parametrize("chunked,batches", [(True, [600]), (False, [600]), (True, [290, 310]), (True, [1, 599]),
                                              (True, [300, 40, 260]), (True, [9000]), (True, [4500, 4500]),
-                                             ("scan", [9000]), ("scan", [300, 40, 260]), ("scan", [4500, 4500])])
+                                             ("scan", [9000]), ("scan", [300, 40, 260]), ("scan", [4500, 4500]),
+                                             ("fast", [9000]), ("fast", [300, 40, 260]), ("fast", [4500, 4500]),
+                                             ("fast", [1, 599])])
 def test_batch_smooth_long_clip_vs_oracle(torch_cuda, chunked, batches):
     """Person count changing, random invalid control points, non-zero r; the chunk-parallel paths (batches of more
     than 256 frames: one pass with a warm-up per chunk by default, "scan" = the chunk scan, 9000 frames = 71 chunks in
@@ -412,6 +414,11 @@ def test_batch_smooth_long_clip_vs_oracle(torch_cuda, chunked, batches):
     rng = np.random.default_rng(77)
     F, P = sum(batches), 3
     fzr = np.stack([rng.uniform(1.0, 3.0, 24), rng.uniform(0.5, 1.0, 24), rng.uniform(0.0, 0.5, 24)], axis=1)
+    if chunked == "fast":
+        # followers that all forget their state within 256 frames (like the shipped blender_smooth_profile.json, f = 1.5 ...
+        # 3, z = 0.75): batches of more than 256 frames take the one-pass path; the slow followers above keep the scan
+        fzr = np.stack([rng.uniform(1.5, 3.0, 24), rng.uniform(0.7, 0.8, 24), rng.uniform(0.0, 0.5, 24)], axis=1)
+        chunked = True
     ctrl = np.cumsum(rng.normal(0, 0.01, (F, P, 24, 4)), axis=0) + rng.uniform(-2, 2, (1, P, 24, 4))
     ctrl[:, :, [k for k in range(24) if k != 1], 3] = 0.0
     vmask = rng.random((F, P, 24)) > 0.05

@@ -155,3 +155,40 @@ def test_c_oracle_smooth_matches_reference(name, split):
         assert nsm[t] == w.shape[0], f"frame {t}"
         if w.size:
             np.testing.assert_allclose(out[t, :nsm[t]], w, rtol=1e-12, atol=1e-14)
+
+
+def _forget_frames(f, z, r, T, limit=256):
+    """Frames after which max|A^n| < 1e-19 for the state matrix of one present frame (what snowtri_smooth_run computes
+    on the host to choose the one-pass path; csrc/snowtri_smooth.cu)."""
+    k1, k2, k3 = z / (np.pi * f), 1 / (2 * np.pi * f) ** 2, r * z / (2 * np.pi * f)
+    g = T / k2
+    A = np.array([[0, 0, 0], [0, 1, T], [-k3 / k2, -g, 1 - g * (T + k1)]])
+    pw = np.eye(3)
+    for n in range(1, limit + 1):
+        pw = A @ pw
+        if np.abs(pw).max() < 1e-19:
+            return n
+    return 0
+
+
+def test_follower_forgets_its_state_and_warm_up_chunks_equal_the_sequential_recurrence():
+    """The one-pass smoothing path: with the reference's default filter a follower has forgotten any
+    start state after 80 present frames, so a chunk that starts from a ZERO state that many frames early gives the
+    sequential recurrence's output on its own frames -- checked here on the CPU with the C oracle as the walker."""
+    from oracle import c_oracle
+    assert _forget_frames(2.5, 0.75, 0.0, 1 / 30) == 80 and _forget_frames(2.0, 0.75, 0.0, 1 / 30) == 95
+    assert _forget_frames(0.01, 0.75, 0.0, 1 / 30) == 0          # a slow filter keeps the chunk scan
+    f, z, r, T = 2.5, 0.75, 0.4, 1 / 30
+    W = _forget_frames(f, z, r, T)
+    assert 0 < W <= 256
+    rng = np.random.default_rng(5)
+    F, P, J, L = 1000, 2, 5, 256
+    pts = rng.uniform(-2, 2, (1, P, 1, 3)) + np.cumsum(rng.normal(0, 0.01, (F, P, J, 3)), axis=0)
+    nout = np.full(F, P, np.int32)
+    want, _, _ = c_oracle.smooth(pts, nout, f, z, r, T)
+    for t0 in range(L, F, L):
+        tw = t0 - W
+        state = np.zeros(2 + 3 * P * J * 3)
+        state[0], state[1] = 1.0, P                                # initialised clip, zero followers
+        got, _, _ = c_oracle.smooth(pts[tw:t0 + L], nout[tw:t0 + L], f, z, r, T, state=state)
+        np.testing.assert_allclose(got[W:], want[t0:t0 + L], rtol=1e-13, atol=1e-15)
