@@ -701,6 +701,33 @@ def test_general_second_generation_thresholds(torch_cuda, prm_over):
         np.testing.assert_allclose(res["pscores"][valid], ref["pscores"][valid], rtol=2e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("noise,prm_over", [(0.0, dict(ast=4e4)), (0.0, dict(ast=2e4, cond_tol=0.05)), (0.0, dict(dthr=1e-5, ast=0.2)),
+                                            (0.02, dict(ast=25.0)), (0.5, dict(dthr=0.0502, ast=0.21))])
+def test_general_matching_bounds_edge_cases(torch_cuda, noise, prm_over):
+    """The matching kernel decides from float32 bounds and falls back to float64 where they cannot decide: noise-free
+    detections (rays that pass within micrometres: joints without an upper bound, heavy-tailed scores, thresholds in
+    the middle of the score distribution), a distance threshold below the float32 error of a ray distance (no joint
+    surely passes), thresholds a hair off the defaults.  The decisions (persons per frame, zero pattern) must be the
+    float64 oracle's in every case."""
+    torch = torch_cuda
+    from oracle import c_oracle
+    rig = synth.ring_rig(8, seed=2)
+    d = synth.make_frames(rig, 32, 4, 133, seed=4242, noise_px=noise, low_score_frac=0.05, drop_prob=0.1)
+    prm = dict(synth.MULTI_PARAMS, **prm_over)
+    pout = 8
+    ref = c_oracle.fused(d["kpts"], d["scores"], d["counts"], rig.K, rig.R, rig.t, prm, Pout=pout)
+    res, kn, ln = _run_general(torch, rig, d, prm, pout, "mixed", 2)
+    assert kn == "general2" and ln == 3
+    assert np.array_equal(res["nout"], ref["nout"])
+    valid = np.arange(pout)[None, :] < np.minimum(ref["nout"], pout)[:, None]
+    assert not res["out"][~valid].any()
+    if valid.any():
+        assert np.array_equal(res["out"][valid][:, :, 3] == 0, ref["kscores"][valid] == 0)
+        assert rel_l2(res["out"][valid][:, :, :3], ref["points"][valid]) < TOL_NORTH_STAR
+        # a candidate kept or dropped differently would change its cluster's member count, i.e. every keypoint score
+        np.testing.assert_allclose(res["out"][valid][:, :, 3], ref["kscores"][valid], rtol=2e-3, atol=1e-7)
+
+
 def test_general_second_generation_chunks_and_truncation(torch_cuda):
     """Several scratch chunks per batch (frames_per_group caps the chunk) and keypoint_num < J give the same bytes /
     the truncated rows of the one-chunk run."""
